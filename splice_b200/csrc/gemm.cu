@@ -1,0 +1,290 @@
+// splice_b200 — bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator,
+// TMA-staged 128B-swizzled operand tiles), with the ViT's elementwise work fused into the epilogue.
+//
+// Replaces, for the frozen DINO ViT of the reference, every cuBLAS call behind
+//   models/extractor.py:83,91,99 (self.model(input_img)): qkv / proj / fc1 / fc2 linears, the patch-embed
+//   conv (k = stride = patch, i.e. a GEMM over patchified pixels), and the dgrad halves of their backward.
+//
+// Kernel shape: one CTA per 128 x BN output tile, 6 warps:
+//   warp 0      TMA producer   (one elected lane; STAGES-deep ring of {A 128x64, B BNx64} bf16 tiles)
+//   warp 1      MMA issuer     (one elected lane; 4 x tcgen05.mma K=16 per stage; owns TMEM alloc/dealloc)
+//   warps 2..5  epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global)
+// Shared memory per CTA is kept <= ~100 KB so that two CTAs are co-resident per SM: while one CTA drains
+// its accumulator through the epilogue, the other one's mainloop keeps the tensor pipe busy.
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+#include "gemm.h"
+
+namespace splice {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr uint32_t A_BYTES = BM * BK * 2;
+    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t TILES_BYTES = STAGES * STAGE_BYTES;
+    static constexpr uint32_t BAR_BYTES = 256;
+    static constexpr uint32_t TOTAL = TILES_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                         int K, GemmEpilogue ep) {
+    using L = GemmSmem<BN, STAGES>;
+    constexpr uint32_t TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + STAGES * L::A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILES_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int num_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                tma_load_2d(smemA + s * L::A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+                tma_load_2d(smemB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + s * L::A_BYTES));
+                const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + s * L::B_BYTES));
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j) {
+                    // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                    umma_bf16_ss(tmem_base, adesc + 2u * j, bdesc + 2u * j, idesc, (kb | j) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col = n0 + c * 32;
+            if (col < N) {  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+                tmem_ld_wait();
+                if (row < M) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    gemm_epilogue_chunk(ep, row, col, v);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check kernel (same operands, same epilogue). Not on the product path: selected only by
+// impl == GEMM_IMPL_SIMT from the unit tests to separate "tcgen05 plumbing" from "epilogue logic".
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gemm_bf16_simt_kernel(const bf16* __restrict__ A, int lda,
+                                                             const bf16* __restrict__ B, int ldb, int M, int N, int K,
+                                                             GemmEpilogue ep) {
+    __shared__ float As[128][33];
+    __shared__ float Bs[32][33];
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 32;
+    const int tid = threadIdx.x;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = tid; i < 128 * 32; i += 128) {
+            const int r = i >> 5, c = i & 31;
+            As[r][c] = (m0 + r < M) ? __bfloat162float(A[(size_t)(m0 + r) * lda + k0 + c]) : 0.f;
+        }
+        for (int i = tid; i < 32 * 32; i += 128) {
+            const int r = i >> 5, c = i & 31;
+            Bs[r][c] = (n0 + r < N) ? __bfloat162float(B[(size_t)(n0 + r) * ldb + k0 + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const float a = As[tid][k];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, Bs[j][k], acc[j]);
+        }
+        __syncthreads();
+    }
+    const int row = m0 + tid;
+    if (row < M && n0 < N) gemm_epilogue_chunk(ep, row, n0, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            return nullptr;
+        }
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64, 128B swizzle.
+static int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc = get_tmap_encoder();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old or no GPU)");
+        return SPLICE_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box_rows=%d ptr=%p", (int)r, rows, cols, ld,
+                  box_rows, (const void*)ptr);
+        return SPLICE_ERR_CUDA;
+    }
+    return SPLICE_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tcgen05(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep,
+                          cudaStream_t stream) {
+    using L = GemmSmem<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPLICE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, STAGES>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+    if (rc) return rc;
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+    gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep);
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
+int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep, int impl,
+                 int bn_hint, cudaStream_t stream) {
+    SPLICE_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    SPLICE_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
+    SPLICE_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+    SPLICE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%d / ldb=%d must be multiples of 8 (16-byte rows)", lda, ldb);
+    SPLICE_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: A/B must be 16-byte aligned");
+    SPLICE_REQUIRE(!ep.c32 || (ep.ldc32 % 4 == 0 && ((uintptr_t)ep.c32 & 15) == 0), "gemm: c32 alignment");
+    SPLICE_REQUIRE(!ep.c16 || (ep.ldc16 % 8 == 0 && ((uintptr_t)ep.c16 & 15) == 0), "gemm: c16 alignment");
+    SPLICE_REQUIRE(!ep.residual || (ep.ldr % 4 == 0 && ((uintptr_t)ep.residual & 15) == 0), "gemm: residual alignment");
+    SPLICE_REQUIRE(!ep.bias || ((uintptr_t)ep.bias & 15) == 0, "gemm: bias alignment");
+    SPLICE_REQUIRE(ep.act == GEMM_ACT_NONE || ep.act == GEMM_ACT_GELU || ep.act == GEMM_ACT_GELU_GRAD, "gemm: bad act %d",
+                   ep.act);
+    SPLICE_REQUIRE(ep.act != GEMM_ACT_GELU_GRAD || ep.aux16, "gemm: GELU_GRAD needs aux16");
+    SPLICE_REQUIRE(!ep.aux16 || (ep.ldaux % 8 == 0 && ((uintptr_t)ep.aux16 & 15) == 0), "gemm: aux16 alignment");
+    SPLICE_REQUIRE(!ep.pos || (ep.ldpos % 4 == 0 && ((uintptr_t)ep.pos & 15) == 0), "gemm: pos alignment");
+    SPLICE_REQUIRE(!ep.slice32 || (ep.slice_c0 % 32 == 0 && ep.slice_c1 % 32 == 0 && ep.ldslice % 4 == 0 &&
+                                   ((uintptr_t)ep.slice32 & 15) == 0),
+                   "gemm: slice32 alignment");
+    SPLICE_REQUIRE(ep.c32 || ep.c16 || ep.slice32, "gemm: no output requested");
+
+    if (impl == GEMM_IMPL_SIMT) {
+        dim3 grid(ceil_div(N, 32), ceil_div(M, 128));
+        gemm_bf16_simt_kernel<<<grid, 128, 0, stream>>>(A, lda, B, ldb, M, N, K, ep);
+        SPLICE_LAUNCH_CHECK();
+        return SPLICE_OK;
+    }
+    SPLICE_REQUIRE(impl == GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
+
+    int bn = bn_hint;
+    if (bn == 0) {
+        // Per-SM work model: the busiest SM executes ceil(tiles / 148) tiles of width c. Narrow tiles are
+        // penalised because a 128 x c MMA re-reads the 128-row A tile from shared memory for fewer FLOPs
+        // (128x64 needs 192 B/clk of smem operand bandwidth, above the 128 B/clk an SM has).
+        const int mt = ceil_div(M, BM);
+        const int cand[3] = {256, 128, 64};
+        const double penalty[3] = {1.0, 1.1, 1.4};
+        double best = 1e30;
+        for (int i = 0; i < 3; ++i) {
+            const int c = cand[i];
+            const long tiles = (long)mt * ceil_div(N, c);
+            const double cost = (double)((tiles + 147) / 148) * c * penalty[i];
+            if (cost < best) { best = cost; bn = c; }
+        }
+    }
+    switch (bn) {
+        case 64:  return launch_tcgen05<64, 4>(A, lda, B, ldb, M, N, K, ep, stream);
+        case 128: return launch_tcgen05<128, 3>(A, lda, B, ldb, M, N, K, ep, stream);
+        case 256: return launch_tcgen05<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
+        default: break;
+    }
+    set_error("gemm: unsupported BN %d", bn);
+    return SPLICE_ERR_ARG;
+}
+
+}  // namespace splice
