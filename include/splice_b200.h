@@ -61,6 +61,91 @@ typedef struct SpliceGemmArgs {
 } SpliceGemmArgs;
 SPLICE_API int splice_gemm_bf16(const SpliceGemmArgs* args, void* stream);
 
+/* ---- per-kernel entry points (parity tests call the same kernels the engine chains) --------------- */
+/* y16 = LayerNorm(x) * gamma + beta, eps; stats [M,2] = (mean, rstd) or NULL.  ref: DINO Block.norm1/norm2 */
+SPLICE_API int splice_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y16, void* stats, int M,
+                                    int D, float eps, void* stream);
+/* g_out = g_in + dLN(dy; x, stats, gamma); g16 = bf16(g_out). g_in may be NULL, g16 may be NULL */
+SPLICE_API int splice_layernorm_bwd(const void* dy, const void* x, const void* stats, const void* gamma, const void* g_in,
+                                    void* g_out, void* g16, int M, int D, void* stream);
+/* o = softmax(q k^T / 8) v per (sequence, head); qkv bf16 [S*t, 3D]; o bf16 [S*t, D]; lse fp32 [S,H,t] (log2 domain).
+ * ref: DINO Attention.forward behind models/extractor.py:83; the probs tap is extractor.py:44-45,57-61 */
+SPLICE_API int splice_attention_fwd(const void* qkv, void* o, void* lse, int S, int t, int D, int H, void* stream);
+SPLICE_API int splice_attention_bwd(const void* qkv, const void* o, const void* dout, const void* lse, void* delta_scratch,
+                                    void* dqkv, int S, int t, int D, int H, void* stream);
+/* torchvision Resize(size, max_size) output size.  ref: util/losses.py:20 */
+SPLICE_API void splice_resized_hw(int h, int w, int size, int max_size, int* oh, int* ow);
+/* img fp32 [3,h,w] -> antialiased resize (oh,ow) -> ImageNet normalise -> patch matrix bf16 rows row0.. (ld 3*p*p).
+ * ref: LossG.global_transform util/losses.py:19-24 + DINO PatchEmbed unfold */
+SPLICE_API int splice_preprocess_fwd(const void* img, int h, int w, int oh, int ow, int patch, void* patches, int row0,
+                                     void* stream);
+SPLICE_API int splice_preprocess_bwd(const void* dpatch, int ldp, int row0, int h, int w, int oh, int ow, int patch,
+                                     void* dimg, void* stream);
+
+/* ---- frozen DINO ViT engine ------------------------------------------------------------------------ */
+/* ref: VitExtractor.__init__ models/extractor.py:19-29 (the hub model), and every `self.model(input_img)`.
+ * `packed_weights` is ONE fp32 device buffer (the same buffer rank 0 broadcasts over NCCL), laid out as
+ *   cls_token[D] pos_embed[n_pos*D] patch_embed.proj.weight[D*3*p*p] patch_embed.proj.bias[D]
+ *   depth x { norm1.weight norm1.bias attn.qkv.weight[3D*D] attn.qkv.bias[3D] attn.proj.weight[D*D] attn.proj.bias
+ *             norm2.weight norm2.bias mlp.fc1.weight[4D*D] mlp.fc1.bias[4D] mlp.fc2.weight[D*4D] mlp.fc2.bias }
+ *   norm.weight[D] norm.bias[D]                                                                              */
+typedef struct SpliceVitDesc {
+    int patch, dim, heads, depth, n_pos;
+    float ln_eps;
+} SpliceVitDesc;
+SPLICE_API size_t splice_vit_packed_floats(const SpliceVitDesc* desc);
+SPLICE_API int splice_vit_create(void** ctx, const SpliceVitDesc* desc, const void* packed_weights, size_t n_floats,
+                                 void* stream);
+SPLICE_API int splice_vit_destroy(void* ctx);
+
+typedef struct SpliceImage {
+    void* data; /* fp32 [3,h,w], pixel range [0,1] (gradient: same shape) */
+    int h, w;
+} SpliceImage;
+
+/* Batched forward of n_images images that share one ViT input size (out_h, out_w).
+ * ref: get_feature_from_input / get_qkv_feature_from_input / get_keys_from_input, models/extractor.py:81-95,153-156 */
+typedef struct SpliceVitForwardArgs {
+    const SpliceImage* images; /* host array */
+    int n_images;
+    int out_h, out_w;      /* resize target = ViT input size, multiples of the patch size */
+    const void* pos;       /* fp32 [1 + gh*gw, D] interpolated pos_embed, NULL = trained grid */
+    int n_grad;            /* activations of the first n_grad images are kept for splice_vit_backward */
+    int slot;              /* 0 or 1: two forward passes may be alive before their backward */
+    void* keys32;          /* out fp32 [n_images*t, D]: layer-11 keys (head h at columns h*64..), or NULL */
+    void* cls32;           /* out fp32 [n_images, D]: block-11 output token 0 (pre final norm), or NULL */
+    void* qkv32_all;       /* out fp32 [depth, n_images*t, 3D] (compat taps), or NULL */
+    void* block32_all;     /* out fp32 [depth, n_images*t, D]  (compat taps), or NULL */
+    int gemm_impl;         /* 0 = tcgen05 */
+} SpliceVitForwardArgs;
+SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* args, void* stream);
+
+/* dgrad-only backward of the first n_grad images of the last forward in `slot`.
+ * ref: loss_G.backward() train.py:78 restricted to the path util/losses.py builds */
+typedef struct SpliceVitBackwardArgs {
+    int slot;
+    const void* dkeys32;       /* fp32 [n_grad*t, D] or NULL */
+    const void* dcls32;        /* fp32 [n_grad, D] or NULL */
+    const SpliceImage* grads;  /* host array, n_grad entries; data = fp32 [3,h,w] out (NULL entry = skip) */
+    int gemm_impl;
+} SpliceVitBackwardArgs;
+SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* args, void* stream);
+
+/* ---- losses ----------------------------------------------------------------------------------------- */
+/* loss[0] = mean((S(keys_x) - S(keys_a))^2), S = cosine self-similarity of the rows of a [t,D] key matrix;
+ * dkeys_x = coef * dloss/dkeys_x (fp32 [t,D]) or NULL.  ref: attn_cosine_sim models/extractor.py:4-9,
+ * get_keys_self_sim_from_input :158-163, calculate_global_ssim_loss util/losses.py:74-83 */
+SPLICE_API int splice_loss_ssim(void* ctx, const void* keys_x, const void* keys_a, int t, float coef, void* dkeys_x,
+                                void* loss, int gemm_impl, void* stream);
+/* loss[0] = mean((a - b)^2) over [rows, cols]; grad = coef * dloss/da or NULL.
+ * ref: calculate_crop_cls_loss util/losses.py:85-94, calculate_global_id_loss :96-105 */
+SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows, int cols, float coef, void* grad,
+                               void* loss, void* stream);
+/* cosine self-similarity matrix fp32 [t,t] of keys fp32 [t,D].  ref: models/extractor.py:158-163 */
+SPLICE_API int splice_keys_self_sim(void* ctx, const void* keys, int t, void* out_tt, int gemm_impl, void* stream);
+/* total[0] = sum_i weights_host[i] * terms[i], n <= 8.  ref: LossG.forward util/losses.py:46-72 */
+SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

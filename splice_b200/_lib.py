@@ -55,6 +55,34 @@ class SpliceGemmArgs(C.Structure):
     ]
 
 
+class SpliceVitDesc(C.Structure):
+    _fields_ = [("patch", c_int), ("dim", c_int), ("heads", c_int), ("depth", c_int), ("n_pos", c_int), ("ln_eps", c_float)]
+
+
+class SpliceImage(C.Structure):
+    _fields_ = [("data", c_void_p), ("h", c_int), ("w", c_int)]
+
+
+class SpliceVitForwardArgs(C.Structure):
+    _fields_ = [
+        ("images", C.POINTER(SpliceImage)), ("n_images", c_int),
+        ("out_h", c_int), ("out_w", c_int),
+        ("pos", c_void_p),
+        ("n_grad", c_int), ("slot", c_int),
+        ("keys32", c_void_p), ("cls32", c_void_p), ("qkv32_all", c_void_p), ("block32_all", c_void_p),
+        ("gemm_impl", c_int),
+    ]
+
+
+class SpliceVitBackwardArgs(C.Structure):
+    _fields_ = [
+        ("slot", c_int),
+        ("dkeys32", c_void_p), ("dcls32", c_void_p),
+        ("grads", C.POINTER(SpliceImage)),
+        ("gemm_impl", c_int),
+    ]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -68,10 +96,39 @@ splice_launch_count = _sig("splice_launch_count", c_longlong, [])
 splice_launch_count_reset = _sig("splice_launch_count_reset", None, [])
 splice_gemm_bf16 = _sig("splice_gemm_bf16", c_int, [C.POINTER(SpliceGemmArgs), c_void_p])
 
+splice_layernorm_fwd = _sig("splice_layernorm_fwd", c_int,
+                            [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p])
+splice_layernorm_bwd = _sig("splice_layernorm_bwd", c_int,
+                            [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p])
+splice_attention_fwd = _sig("splice_attention_fwd", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
+splice_attention_bwd = _sig("splice_attention_bwd", c_int,
+                            [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
+splice_resized_hw = _sig("splice_resized_hw", None, [c_int, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)])
+splice_preprocess_fwd = _sig("splice_preprocess_fwd", c_int,
+                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p])
+splice_preprocess_bwd = _sig("splice_preprocess_bwd", c_int,
+                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+splice_vit_packed_floats = _sig("splice_vit_packed_floats", c_size_t, [C.POINTER(SpliceVitDesc)])
+splice_vit_create = _sig("splice_vit_create", c_int,
+                         [C.POINTER(c_void_p), C.POINTER(SpliceVitDesc), c_void_p, c_size_t, c_void_p])
+splice_vit_destroy = _sig("splice_vit_destroy", c_int, [c_void_p])
+splice_vit_forward = _sig("splice_vit_forward", c_int, [c_void_p, C.POINTER(SpliceVitForwardArgs), c_void_p])
+splice_vit_backward = _sig("splice_vit_backward", c_int, [c_void_p, C.POINTER(SpliceVitBackwardArgs), c_void_p])
+splice_loss_ssim = _sig("splice_loss_ssim", c_int,
+                        [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p])
+splice_loss_mse = _sig("splice_loss_mse", c_int,
+                       [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p])
+splice_keys_self_sim = _sig("splice_keys_self_sim", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p])
+splice_weighted_total = _sig("splice_weighted_total", c_int, [c_void_p, C.POINTER(c_float), c_int, c_void_p, c_void_p])
+
 # every symbol include/splice_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "splice_version", "splice_last_error", "splice_launch_count", "splice_launch_count_reset",
     "splice_gemm_bf16",
+    "splice_layernorm_fwd", "splice_layernorm_bwd", "splice_attention_fwd", "splice_attention_bwd",
+    "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd",
+    "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
+    "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
 ]
 
 

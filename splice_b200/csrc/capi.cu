@@ -5,9 +5,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include "attention.h"
 #include "common.cuh"
+#include "elementwise.h"
 #include "gemm.h"
+#include "losses.h"
+#include "preprocess.h"
 #include "splice_b200.h"
+#include "vit.h"
 
 namespace splice {
 
@@ -49,6 +54,173 @@ SPLICE_API int splice_gemm_bf16(const SpliceGemmArgs* a, void* stream) {
     ep.slice_c0 = a->slice_c0; ep.slice_c1 = a->slice_c1; ep.ldslice = a->ldslice;
     return gemm_bf16_tn(static_cast<const bf16*>(a->A), a->lda, static_cast<const bf16*>(a->B), a->ldb, a->M, a->N, a->K,
                         ep, a->impl, a->bn_hint, static_cast<cudaStream_t>(stream));
+}
+
+// ---- per-kernel entry points ---------------------------------------------------------------------
+SPLICE_API int splice_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y16, void* stats, int M, int D,
+                                    float eps, void* stream) {
+    return layernorm_fwd((const float*)x, (const float*)gamma, (const float*)beta, (bf16*)y16, (float*)stats, M, D, eps,
+                         (cudaStream_t)stream);
+}
+SPLICE_API int splice_layernorm_bwd(const void* dy, const void* x, const void* stats, const void* gamma, const void* g_in,
+                                    void* g_out, void* g16, int M, int D, void* stream) {
+    return layernorm_bwd((const float*)dy, (const float*)x, (const float*)stats, (const float*)gamma, (const float*)g_in,
+                         (float*)g_out, (bf16*)g16, M, D, (cudaStream_t)stream);
+}
+SPLICE_API int splice_attention_fwd(const void* qkv, void* o, void* lse, int S, int t, int D, int H, void* stream) {
+    return attention_fwd((const bf16*)qkv, (bf16*)o, (float*)lse, S, t, D, H, (cudaStream_t)stream);
+}
+SPLICE_API int splice_attention_bwd(const void* qkv, const void* o, const void* dout, const void* lse, void* delta_scratch,
+                                    void* dqkv, int S, int t, int D, int H, void* stream) {
+    return attention_bwd((const bf16*)qkv, (const bf16*)o, (const bf16*)dout, (const float*)lse, (float*)delta_scratch,
+                         (bf16*)dqkv, S, t, D, H, (cudaStream_t)stream);
+}
+SPLICE_API void splice_resized_hw(int h, int w, int size, int max_size, int* oh, int* ow) {
+    resized_hw(h, w, size, max_size, oh, ow);
+}
+SPLICE_API int splice_preprocess_fwd(const void* img, int h, int w, int oh, int ow, int patch, void* patches, int row0,
+                                     void* stream) {
+    return preprocess_fwd((const float*)img, h, w, oh, ow, patch, (bf16*)patches, row0, (cudaStream_t)stream);
+}
+SPLICE_API int splice_preprocess_bwd(const void* dpatch, int ldp, int row0, int h, int w, int oh, int ow, int patch,
+                                     void* dimg, void* stream) {
+    return preprocess_bwd((const float*)dpatch, ldp, row0, h, w, oh, ow, patch, (float*)dimg, (cudaStream_t)stream);
+}
+
+// ---- ViT engine ----------------------------------------------------------------------------------
+static VitDesc to_desc(const SpliceVitDesc* d) {
+    VitDesc v;
+    v.patch = d->patch; v.dim = d->dim; v.heads = d->heads; v.depth = d->depth; v.n_pos = d->n_pos; v.ln_eps = d->ln_eps;
+    return v;
+}
+SPLICE_API size_t splice_vit_packed_floats(const SpliceVitDesc* desc) { return desc ? VitEngine::packed_size(to_desc(desc)) : 0; }
+SPLICE_API int splice_vit_create(void** ctx, const SpliceVitDesc* desc, const void* packed_weights, size_t n_floats,
+                                 void* stream) {
+    SPLICE_REQUIRE(ctx && desc && packed_weights, "splice_vit_create: null argument");
+    VitEngine* e = nullptr;
+    int rc = VitEngine::create(&e, to_desc(desc), (const float*)packed_weights, n_floats, (cudaStream_t)stream);
+    if (rc) return rc;
+    *ctx = e;
+    return SPLICE_OK;
+}
+SPLICE_API int splice_vit_destroy(void* ctx) {
+    delete static_cast<VitEngine*>(ctx);
+    return SPLICE_OK;
+}
+SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* a, void* stream) {
+    SPLICE_REQUIRE(ctx && a, "splice_vit_forward: null argument");
+    SPLICE_REQUIRE(a->n_images > 0 && a->n_images <= 64 && a->images, "splice_vit_forward: n_images out of range");
+    ImageRef imgs[64];
+    for (int i = 0; i < a->n_images; ++i) imgs[i] = ImageRef{(const float*)a->images[i].data, a->images[i].h, a->images[i].w};
+    VitForwardArgs v;
+    v.images = imgs; v.n_images = a->n_images; v.out_h = a->out_h; v.out_w = a->out_w; v.pos = (const float*)a->pos;
+    v.n_grad = a->n_grad; v.slot = a->slot; v.keys32 = (float*)a->keys32; v.cls32 = (float*)a->cls32;
+    v.qkv32_all = (float*)a->qkv32_all; v.block32_all = (float*)a->block32_all; v.gemm_impl = a->gemm_impl;
+    return static_cast<VitEngine*>(ctx)->forward(v, (cudaStream_t)stream);
+}
+SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, void* stream) {
+    SPLICE_REQUIRE(ctx && a && a->grads, "splice_vit_backward: null argument");
+    VitEngine* e = static_cast<VitEngine*>(ctx);
+    SPLICE_REQUIRE(a->slot == 0 || a->slot == 1, "splice_vit_backward: slot must be 0 or 1");
+    const int n = e->slot_n_grad(a->slot);
+    SPLICE_REQUIRE(n > 0 && n <= 64, "splice_vit_backward: slot %d holds no forward pass with n_grad > 0", a->slot);
+    ImageGradRef g[64];
+    for (int i = 0; i < n; ++i) g[i] = ImageGradRef{(float*)a->grads[i].data, a->grads[i].h, a->grads[i].w};
+    VitBackwardArgs v;
+    v.slot = a->slot; v.dkeys32 = (const float*)a->dkeys32; v.dcls32 = (const float*)a->dcls32; v.gemm_impl = a->gemm_impl;
+    v.grads = g;
+    return e->backward(v, (cudaStream_t)stream);
+}
+
+// ---- losses --------------------------------------------------------------------------------------
+namespace {
+struct SsimWs {
+    bf16 *ax, *bx, *aa, *ba, *khT, *E16;
+    float *Sx, *Sa, *R, *inv_x, *inv_a, *c, *row_loss;
+    int tp;
+};
+int carve_ssim(VitEngine* e, int t, SsimWs* w) {
+    void* p; size_t bytes;
+    int rc = e->loss_scratch(t, &p, &bytes);
+    if (rc) return rc;
+    const size_t tp = (size_t)((t + 63) / 64) * 64, D = e->desc().dim;
+    uint8_t* b = static_cast<uint8_t*>(p);
+    auto take = [&](size_t n) { uint8_t* r = b; b += (n + 255) & ~(size_t)255; return r; };
+    w->tp = (int)tp;
+    w->ax = (bf16*)take(tp * 3 * D * 2); w->bx = (bf16*)take(tp * 3 * D * 2);
+    w->aa = (bf16*)take(tp * 3 * D * 2); w->ba = (bf16*)take(tp * 3 * D * 2);
+    w->khT = (bf16*)take(D * tp * 2);
+    w->Sx = (float*)take(tp * tp * 4); w->Sa = (float*)take(tp * tp * 4);
+    w->E16 = (bf16*)take(tp * tp * 2);
+    w->R = (float*)take(tp * D * 4);
+    w->inv_x = (float*)take(tp * 4); w->inv_a = (float*)take(tp * 4); w->c = (float*)take(tp * 4); w->row_loss = (float*)take(tp * 4);
+    if ((size_t)(b - static_cast<uint8_t*>(p)) > bytes) {
+        set_error("loss scratch carve overflow");
+        return SPLICE_ERR_STATE;
+    }
+    return SPLICE_OK;
+}
+int gram(const bf16* a, const bf16* b, int t, int tp, int D, float* S, int impl, cudaStream_t st) {
+    GemmEpilogue ep;
+    ep.c32 = S; ep.ldc32 = tp;
+    return gemm_bf16_tn(a, 3 * D, b, 3 * D, t, tp, 3 * D, ep, impl, 0, st);
+}
+}  // namespace
+
+SPLICE_API int splice_loss_ssim(void* ctx, const void* keys_x, const void* keys_a, int t, float coef, void* dkeys_x,
+                                void* loss, int gemm_impl, void* stream) {
+    SPLICE_REQUIRE(ctx && keys_x && keys_a && loss && t > 0, "splice_loss_ssim: bad argument");
+    VitEngine* e = static_cast<VitEngine*>(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = e->desc().dim;
+    SsimWs w;
+    int rc = carve_ssim(e, t, &w); if (rc) return rc;
+    const float* kx = (const float*)keys_x; const float* ka = (const float*)keys_a;
+    if ((rc = selfsim_prep(kx, D, t, D, w.ax, w.bx, w.inv_x, st))) return rc;
+    if ((rc = selfsim_prep(ka, D, t, D, w.aa, w.ba, w.inv_a, st))) return rc;
+    if ((rc = gram(w.ax, w.bx, t, w.tp, D, w.Sx, gemm_impl, st))) return rc;
+    if ((rc = gram(w.aa, w.ba, t, w.tp, D, w.Sa, gemm_impl, st))) return rc;
+    if ((rc = selfsim_err(w.Sx, w.Sa, w.tp, t, w.E16, w.tp, w.c, w.row_loss, st))) return rc;
+    if ((rc = reduce_sum(w.row_loss, t, 1.f, (float*)loss, st))) return rc;
+    if (dkeys_x) {
+        if ((rc = selfsim_transpose(kx, D, w.inv_x, t, D, w.khT, w.tp, st))) return rc;
+        GemmEpilogue ep;
+        ep.c32 = w.R; ep.ldc32 = D;
+        if ((rc = gemm_bf16_tn(w.E16, w.tp, w.khT, w.tp, t, D, w.tp, ep, gemm_impl, 0, st))) return rc;
+        if ((rc = selfsim_grad(w.R, D, kx, D, w.inv_x, w.c, coef, (float*)dkeys_x, D, t, D, st))) return rc;
+    }
+    return SPLICE_OK;
+}
+
+SPLICE_API int splice_keys_self_sim(void* ctx, const void* keys, int t, void* out_tt, int gemm_impl, void* stream) {
+    SPLICE_REQUIRE(ctx && keys && out_tt && t > 0, "splice_keys_self_sim: bad argument");
+    VitEngine* e = static_cast<VitEngine*>(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = e->desc().dim;
+    SsimWs w;
+    int rc = carve_ssim(e, t, &w); if (rc) return rc;
+    if ((rc = selfsim_prep((const float*)keys, D, t, D, w.ax, w.bx, w.inv_x, st))) return rc;
+    if ((rc = gram(w.ax, w.bx, t, w.tp, D, w.Sx, gemm_impl, st))) return rc;
+    SPLICE_CHECK_CUDA(cudaMemcpy2DAsync(out_tt, (size_t)t * 4, w.Sx, (size_t)w.tp * 4, (size_t)t * 4, t, cudaMemcpyDeviceToDevice, st));
+    return SPLICE_OK;
+}
+
+SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows, int cols, float coef, void* grad, void* loss,
+                               void* stream) {
+    SPLICE_REQUIRE(ctx && a && b && loss && rows > 0 && cols > 0, "splice_loss_mse: bad argument");
+    VitEngine* e = static_cast<VitEngine*>(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    void* p; size_t bytes;
+    int rc = e->loss_scratch(rows > 64 ? rows : 64, &p, &bytes); if (rc) return rc;
+    SPLICE_REQUIRE((size_t)rows * 4 <= bytes, "splice_loss_mse: too many rows");
+    float* row_loss = (float*)p;
+    const float inv = 1.f / ((float)rows * (float)cols);
+    if ((rc = mse_rows((const float*)a, cols, (const float*)b, cols, rows, cols, inv, coef, (float*)grad, cols, row_loss, st))) return rc;
+    return reduce_sum(row_loss, rows, 1.f, (float*)loss, st);
+}
+
+SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream) {
+    return weighted_total((const float*)terms, weights_host, n, (float*)total, (cudaStream_t)stream);
 }
 
 }  // extern "C"

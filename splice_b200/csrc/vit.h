@@ -1,0 +1,85 @@
+// splice_b200 — frozen DINO ViT engine (forward with feature taps + dgrad-only backward), see vit.cu
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace splice {
+
+struct VitDesc {
+    int patch = 8, dim = 768, heads = 12, depth = 12, n_pos = 785;
+    float ln_eps = 1e-6f;
+};
+
+struct ImageRef { const float* data; int h, w; };
+struct ImageGradRef { float* data; int h, w; };
+
+struct VitForwardArgs {
+    const ImageRef* images = nullptr;
+    int n_images = 0;
+    int out_h = 0, out_w = 0;
+    const float* pos = nullptr;       // [1 + gh*gw, D] or nullptr = native pos_embed
+    int n_grad = 0;
+    int slot = 0;
+    float* keys32 = nullptr;          // [n_images*t, D]
+    float* cls32 = nullptr;           // [n_images, D]
+    float* qkv32_all = nullptr;       // [depth, n_images*t, 3D]   (compat taps)
+    float* block32_all = nullptr;     // [depth, n_images*t, D]    (compat taps)
+    int gemm_impl = 0;                // 0 = tcgen05, 1 = SIMT cross-check
+};
+
+struct VitBackwardArgs {
+    int slot = 0;
+    const float* dkeys32 = nullptr;   // [n_grad*t, D]
+    const float* dcls32 = nullptr;    // [n_grad, D]
+    const ImageGradRef* grads = nullptr;  // n_grad entries
+    int gemm_impl = 0;
+};
+
+class VitEngine {
+public:
+    static int create(VitEngine** out, const VitDesc& d, const float* packed_dev, size_t n_floats, cudaStream_t stream);
+    ~VitEngine();
+    static size_t packed_size(const VitDesc& d);
+    int forward(const VitForwardArgs& a, cudaStream_t stream);
+    int backward(const VitBackwardArgs& a, cudaStream_t stream);
+    const VitDesc& desc() const { return d_; }
+    int slot_n_grad(int slot) const { return slots_[slot].pool ? slots_[slot].n_grad : 0; }
+    // scratch for the loss kernels, sized for sequences of up to t tokens (grown on demand)
+    int loss_scratch(int t, void** ptr, size_t* bytes);
+
+private:
+    struct LayerW {
+        const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
+        const bf16 *qkv_w, *qkv_wT, *proj_w, *proj_wT, *fc1_w, *fc1_wT, *fc2_w, *fc2_wT;
+    };
+    struct Slot {
+        int S = 0, t = 0, gh = 0, gw = 0, n_grad = 0, oh = 0, ow = 0;
+        bool pos_custom = false;
+        std::vector<ImageRef> imgs;
+        void* pool = nullptr;
+        size_t pool_bytes = 0;
+        // carved from pool
+        bf16* patches = nullptr;             // [S*(t-1), 3pp]
+        std::vector<float*> x0, x1;          // x0[depth+1], x1[depth]   [M, D]
+        std::vector<bf16*> qkv, o, hpre;     // per layer
+        std::vector<float*> lse, st1, st2;   // per layer
+        bf16 *a16 = nullptr, *h16 = nullptr;
+        // backward
+        float *g = nullptr, *da = nullptr, *delta = nullptr, *dpatch = nullptr;
+        bf16 *g16 = nullptr, *dh16 = nullptr, *do16 = nullptr, *dqkv16 = nullptr;
+    };
+    int configure(Slot& s, int S, int t, int n_grad);
+
+    VitDesc d_;
+    float* w32_ = nullptr;
+    bf16* w16_ = nullptr;
+    const float *cls_ = nullptr, *pos_ = nullptr, *pe_b_ = nullptr, *norm_g_ = nullptr, *norm_b_ = nullptr;
+    const bf16 *pe_w_ = nullptr, *pe_wT_ = nullptr;
+    std::vector<LayerW> L_;
+    Slot slots_[2];
+    void* loss_ws_ = nullptr;
+    size_t loss_ws_bytes_ = 0;
+};
+
+}  // namespace splice

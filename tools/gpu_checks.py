@@ -200,6 +200,269 @@ def gemm_tc_timing():
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------
+# row kernels, attention, preprocessing
+# ------------------------------------------------------------------------------------------------
+def _oracle_on_gpu():
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from oracle import dino_vit, splice_ref
+
+    return dino_vit, splice_ref
+
+
+@check
+def layernorm_fwd_bwd():
+    import torch
+    from splice_b200 import _lib
+    from splice_b200._lib import check as ck, cur_stream, ptr
+
+    out = []
+    for (M, D) in ((785, 768), (3140, 768), (394, 384), (5, 128)):
+        g = torch.Generator(device="cuda").manual_seed(M)
+        x = torch.randn(M, D, device="cuda", generator=g) * 2 + 0.5
+        gamma = torch.randn(D, device="cuda", generator=g)
+        beta = torch.randn(D, device="cuda", generator=g)
+        y16 = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+        stats = torch.empty(M, 2, device="cuda")
+        ck(_lib.splice_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y16), ptr(stats), M, D, 1e-6, cur_stream()))
+        xr = x.clone().requires_grad_(True)
+        ref = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6)
+        dy = torch.randn(M, D, device="cuda", generator=g)
+        gin = torch.randn(M, D, device="cuda", generator=g)
+        ref.backward(dy)
+        gout = torch.empty(M, D, device="cuda")
+        g16 = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+        ck(_lib.splice_layernorm_bwd(ptr(dy), ptr(x), ptr(stats), ptr(gamma), ptr(gin), ptr(gout), ptr(g16), M, D, cur_stream()))
+        torch.cuda.synchronize()
+        r = {"M": M, "D": D, "fwd_rel": _rel(y16, ref), "bwd_rel": _rel(gout, gin + xr.grad), "g16_rel": _rel(g16, gin + xr.grad),
+             "mean_err": _maxabs(stats[:, 0], x.mean(1))}
+        r["ok"] = r["fwd_rel"] < 4e-3 and r["bwd_rel"] < 1e-5 and r["g16_rel"] < 4e-3 and r["mean_err"] < 1e-5
+        out.append(r)
+    return out
+
+
+def _attn_ref(qkv, S, t, D, H):
+    import torch
+
+    q, k, v = qkv.float().reshape(S, t, 3, H, D // H).permute(2, 0, 3, 1, 4)
+    p = ((q @ k.transpose(-2, -1)) * 0.125).softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(S * t, D)
+
+
+@check
+def attention_fwd_bwd():
+    import torch
+    from splice_b200 import _lib
+    from splice_b200._lib import check as ck, cur_stream, ptr
+
+    out = []
+    for (S, t, H) in ((1, 64, 1), (2, 100, 2), (1, 197, 6), (2, 785, 12), (1, 1037, 12)):
+        D = 64 * H
+        g = torch.Generator(device="cuda").manual_seed(t)
+        qkv = (torch.randn(S * t, 3 * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+        o = torch.zeros(S * t, D, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(S, H, t, device="cuda")
+        ck(_lib.splice_attention_fwd(ptr(qkv), ptr(o), ptr(lse), S, t, D, H, cur_stream()))
+        x = qkv.float().requires_grad_(True)
+        ref = _attn_ref(x, S, t, D, H)
+        do = (torch.randn(S * t, D, device="cuda", generator=g)).to(torch.bfloat16)
+        ref.backward(do.float())
+        delta = torch.zeros(S, H, t, device="cuda")
+        dqkv = torch.full((S * t, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ck(_lib.splice_attention_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dqkv), S, t, D, H, cur_stream()))
+        torch.cuda.synchronize()
+        r = {"S": S, "t": t, "H": H, "fwd_rel": _rel(o, ref), "dq_rel": _rel(dqkv[:, :D], x.grad[:, :D]),
+             "dk_rel": _rel(dqkv[:, D:2 * D], x.grad[:, D:2 * D]), "dv_rel": _rel(dqkv[:, 2 * D:], x.grad[:, 2 * D:]),
+             "nan": int(torch.isnan(dqkv.float()).sum().item())}
+        r["ok"] = r["fwd_rel"] < 6e-3 and r["dq_rel"] < 1.5e-2 and r["dk_rel"] < 1.5e-2 and r["dv_rel"] < 1.5e-2 and r["nan"] == 0
+        out.append(r)
+    return out
+
+
+@check
+def preprocess_fwd_bwd():
+    import torch
+    from splice_b200 import _lib
+    from splice_b200._lib import check as ck, cur_stream, ptr
+
+    _, R = _oracle_on_gpu()
+    out = []
+    for (h, w, size, patch) in ((224, 224, 224, 8), (213, 213, 224, 8), (128, 128, 224, 16), (448, 448, 224, 8),
+                                (225, 300, 224, 8), (900, 640, 224, 16)):
+        g = torch.Generator(device="cuda").manual_seed(h * 1000 + w)
+        img = torch.rand(3, h, w, device="cuda", generator=g)
+        oh, ow = R.resized_hw(h, w, size, 480)
+        oh_p, ow_p = oh - oh % patch, ow - ow % patch  # the engine only accepts multiples of the patch
+        if (oh_p, ow_p) != (oh, ow):
+            out.append({"h": h, "w": w, "skip": "not patch-aligned", "ok": True})
+            continue
+        gh, gw = oh // patch, ow // patch
+        pp3 = 3 * patch * patch
+        patches = torch.zeros(gh * gw, pp3, device="cuda", dtype=torch.bfloat16)
+        ck(_lib.splice_preprocess_fwd(ptr(img), h, w, oh, ow, patch, ptr(patches), 0, cur_stream()))
+        x = img.clone().requires_grad_(True)
+        tr = R.global_transform(x, size)
+        ref = torch.nn.functional.unfold(tr[None], patch, stride=patch)[0].t()  # [gh*gw, 3*p*p]
+        dp = torch.randn(gh * gw, pp3, device="cuda", generator=g)
+        ref.backward(dp)
+        dimg = torch.full((3, h, w), float("nan"), device="cuda")
+        ck(_lib.splice_preprocess_bwd(ptr(dp), pp3, 0, h, w, oh, ow, patch, ptr(dimg), cur_stream()))
+        torch.cuda.synchronize()
+        r = {"h": h, "w": w, "oh": oh, "ow": ow, "fwd_maxabs": _maxabs(patches, ref), "bwd_rel": _rel(dimg, x.grad)}
+        r["ok"] = r["fwd_maxabs"] < 2e-2 and r["bwd_rel"] < 1e-5
+        out.append(r)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ViT engine vs oracle
+# ------------------------------------------------------------------------------------------------
+def _engine(name, impl=0):
+    import torch
+    from splice_b200.engine import VitEngine
+
+    dino_vit, R = _oracle_on_gpu()
+    model = dino_vit.build(name).cuda()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    return VitEngine(name, sd, gemm_impl=impl), sd, R
+
+
+def _vit_forward_case(name, hw_list, out_hw, impl=0):
+    import torch
+
+    eng, sd, R = _engine(name, impl)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    imgs = [torch.rand(3, h, w, device="cuda", generator=g) for (h, w) in hw_list]
+    res = eng.forward(imgs, out_hw, n_grad=0, want_all_qkv=True, want_all_blocks=True)
+    torch.cuda.synchronize()
+    rows = []
+    size = min(out_hw)
+    for i, im in enumerate(imgs):
+        with torch.no_grad():
+            taps = R.vit_taps(sd, R.global_transform(im, size)[None])
+        H = eng.heads
+        ref_keys = R.keys_from_qkv(taps["qkv"][11], H).transpose(0, 1).reshape(-1, eng.dim)
+        r = {"model": name, "img": i, "hw": hw_list[i], "impl": impl,
+             "keys_rel": _rel(res["keys"][i], ref_keys), "cls_rel": _rel(res["cls"][i], taps["block"][-1][0, 0]),
+             "qkv0_rel": _rel(res["qkv"][0, i], taps["qkv"][0][0]), "qkv11_rel": _rel(res["qkv"][11, i], taps["qkv"][11][0]),
+             "block0_rel": _rel(res["block"][0, i], taps["block"][0][0]), "block11_rel": _rel(res["block"][11, i], taps["block"][11][0])}
+        r["ok"] = all(v < 2e-2 for k, v in r.items() if k.endswith("_rel"))
+        rows.append(r)
+    return rows
+
+
+@check
+def vit_forward_s16():
+    return _vit_forward_case("dino_vits16", [(224, 224), (213, 213), (128, 128)], (224, 224))
+
+
+@check
+def vit_forward_s16_simt():
+    return _vit_forward_case("dino_vits16", [(224, 224)], (224, 224), impl=1)
+
+
+@check
+def vit_forward_b8():
+    return _vit_forward_case("dino_vitb8", [(224, 224), (220, 220)], (224, 224))
+
+
+@check
+def vit_forward_nonsquare():
+    return _vit_forward_case("dino_vits16", [(225, 300)], (224, 298 - 298 % 16))
+
+
+@check
+def loss_kernels():
+    import torch
+
+    eng, sd, R = _engine("dino_vits16")
+    out = []
+    for t in (197, 785):
+        D = eng.dim
+        g = torch.Generator(device="cuda").manual_seed(t)
+        kx = torch.randn(t, D, device="cuda", generator=g) + 0.3
+        ka = kx + 0.2 * torch.randn(t, D, device="cuda", generator=g)
+        loss = torch.zeros(1, device="cuda")
+        dk = torch.zeros(t, D, device="cuda")
+        eng.loss_ssim(kx, ka, 1.7, loss, dk)
+        x = kx.clone().requires_grad_(True)
+        ref = torch.nn.functional.mse_loss(R.attn_cosine_sim(x[None, None]), R.attn_cosine_sim(ka[None, None]))
+        (1.7 * ref).backward()
+        S = eng.keys_self_sim(kx)
+        torch.cuda.synchronize()
+        r = {"t": t, "ssim_loss": loss.item(), "ref": ref.item(), "loss_rel": abs(loss.item() - ref.item()) / ref.item(),
+             "grad_rel": _rel(dk, x.grad), "S_maxabs": _maxabs(S, R.attn_cosine_sim(kx[None, None])[0])}
+        r["ok"] = r["loss_rel"] < 1e-3 and r["grad_rel"] < 1e-2 and r["S_maxabs"] < 1e-4
+        out.append(r)
+        l2 = torch.zeros(1, device="cuda")
+        gk = torch.zeros(t, D, device="cuda")
+        eng.loss_mse(kx, ka, 0.5, l2, gk)
+        x = kx.clone().requires_grad_(True)
+        ref2 = torch.nn.functional.mse_loss(x, ka)
+        (0.5 * ref2).backward()
+        torch.cuda.synchronize()
+        r = {"t": t, "mse_rel": abs(l2.item() - ref2.item()) / ref2.item(), "mse_grad_rel": _rel(gk, x.grad)}
+        r["ok"] = r["mse_rel"] < 1e-5 and r["mse_grad_rel"] < 1e-5
+        out.append(r)
+    return out
+
+
+def _vit_loss_backward_case(name, hx, hy, impl=0):
+    """Steady-state objective (ssim + 10 cls + id) through the engine vs the oracle's autograd."""
+    import torch
+
+    eng, sd, R = _engine(name, impl)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.rand(3, hx, hx, device="cuda", generator=g)
+    B = torch.rand(3, hy, hy, device="cuda", generator=g)
+    X = (A + 0.1 * torch.randn(3, hx, hx, device="cuda", generator=g)).clamp(0, 1)
+    Y = (B + 0.1 * torch.randn(3, hy, hy, device="cuda", generator=g)).clamp(0, 1)
+    lam = {"ssim": 1.0, "cls": 10.0, "id": 1.0}
+    # engine: sequences ordered [x, y, A, B], the first two keep activations
+    res = eng.forward([X, Y, A, B], (224, 224), n_grad=2)
+    t, D = res["keys"].shape[1], eng.dim
+    terms = torch.zeros(3, device="cuda")
+    dkeys = torch.zeros(2, t, D, device="cuda")
+    dcls = torch.zeros(2, D, device="cuda")
+    eng.loss_ssim(res["keys"][0], res["keys"][2], lam["ssim"], terms[0:1], dkeys[0])
+    eng.loss_mse(res["cls"][0], res["cls"][3], lam["cls"], terms[1:2], dcls[0])
+    eng.loss_mse(res["keys"][1], res["keys"][3], lam["id"], terms[2:3], dkeys[1])
+    dX, dY = eng.backward(0, dkeys, dcls)
+    torch.cuda.synchronize()
+    # oracle
+    xo, yo = X.clone().requires_grad_(True), Y.clone().requires_grad_(True)
+    l_ssim = R.ssim_loss(sd, xo[None], A[None])
+    l_cls = R.cls_loss(sd, xo[None], B[None])
+    l_id = R.id_loss(sd, yo[None], B[None])
+    (lam["ssim"] * l_ssim + lam["cls"] * l_cls + lam["id"] * l_id).backward()
+    r = {"model": name, "hx": hx, "hy": hy, "impl": impl,
+         "ssim": terms[0].item(), "ssim_ref": l_ssim.item(), "cls": terms[1].item(), "cls_ref": l_cls.item(),
+         "id": terms[2].item(), "id_ref": l_id.item(), "dX_rel": _rel(dX, xo.grad), "dY_rel": _rel(dY, yo.grad)}
+    r["loss_rel"] = max(abs(r["ssim"] - r["ssim_ref"]) / abs(r["ssim_ref"]), abs(r["cls"] - r["cls_ref"]) / abs(r["cls_ref"]),
+                        abs(r["id"] - r["id_ref"]) / abs(r["id_ref"]))
+    r["ok"] = r["loss_rel"] < 5e-3 and r["dX_rel"] < 2e-2 and r["dY_rel"] < 2e-2
+    return [r]
+
+
+@check
+def vit_loss_backward_s16():
+    return _vit_loss_backward_case("dino_vits16", 128, 125)
+
+
+@check
+def vit_loss_backward_s16_simt():
+    return _vit_loss_backward_case("dino_vits16", 128, 125, impl=1)
+
+
+@check
+def vit_loss_backward_b8():
+    return _vit_loss_backward_case("dino_vitb8", 224, 217)
+
+
 # ------------------------------------------------------------------------------------------------
 def _run_one(name: str) -> int:
     t0 = time.time()
