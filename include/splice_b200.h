@@ -78,9 +78,11 @@ SPLICE_API void splice_resized_hw(int h, int w, int size, int max_size, int* oh,
 /* img fp32 [3,h,w] -> antialiased resize (oh,ow) -> ImageNet normalise -> patch matrix bf16 rows row0.. (ld 3*p*p).
  * ref: LossG.global_transform util/losses.py:19-24 + DINO PatchEmbed unfold */
 SPLICE_API int splice_preprocess_fwd(const void* img, int h, int w, int oh, int ow, int patch, void* patches, int row0,
-                                     void* stream);
+                                     int normalize, void* stream);
+/* out fp32 [3,oh,ow] = Normalize(Resize(img)) as a plain image.  ref: LossG.global_transform util/losses.py:19-24 */
+SPLICE_API int splice_resize_normalize(const void* img, int h, int w, int oh, int ow, void* out, int normalize, void* stream);
 SPLICE_API int splice_preprocess_bwd(const void* dpatch, int ldp, int row0, int h, int w, int oh, int ow, int patch,
-                                     void* dimg, void* stream);
+                                     void* dimg, int normalize, void* stream);
 
 /* ---- frozen DINO ViT engine ------------------------------------------------------------------------ */
 /* ref: VitExtractor.__init__ models/extractor.py:19-29 (the hub model), and every `self.model(input_img)`.
@@ -108,7 +110,7 @@ typedef struct SpliceImage {
 typedef struct SpliceVitForwardArgs {
     const SpliceImage* images; /* host array */
     int n_images;
-    int out_h, out_w;      /* resize target = ViT input size, multiples of the patch size */
+    int out_h, out_w;      /* resize target = ViT input size; trailing out % patch pixels are dropped like the patch conv does */
     const void* pos;       /* fp32 [1 + gh*gw, D] interpolated pos_embed, NULL = trained grid */
     int n_grad;            /* activations of the first n_grad images are kept for splice_vit_backward */
     int slot;              /* 0 or 1: two forward passes may be alive before their backward */
@@ -117,6 +119,7 @@ typedef struct SpliceVitForwardArgs {
     void* qkv32_all;       /* out fp32 [depth, n_images*t, 3D] (compat taps), or NULL */
     void* block32_all;     /* out fp32 [depth, n_images*t, D]  (compat taps), or NULL */
     int gemm_impl;         /* 0 = tcgen05 */
+    int pre_normalized;    /* 1 = images are already ImageNet-normalised (VitExtractor API), skip (x-mean)/std */
 } SpliceVitForwardArgs;
 SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* args, void* stream);
 
@@ -145,6 +148,13 @@ SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows
 SPLICE_API int splice_keys_self_sim(void* ctx, const void* keys, int t, void* out_tt, int gemm_impl, void* stream);
 /* total[0] = sum_i weights_host[i] * terms[i], n <= 8.  ref: LossG.forward util/losses.py:46-72 */
 SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream);
+
+/* ---- optimiser -------------------------------------------------------------------------------------- */
+/* One Adam step over n_tensors fp32 tensors (host arrays of device pointers / element counts).
+ * `step` is the 1-based step count AFTER the increment.  ref: get_optimizer util/util.py:28-32 -> torch.optim.Adam */
+SPLICE_API int splice_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                                const int* numel, int n_tensors, int step, float lr, float beta1, float beta2, float eps,
+                                void* stream);
 
 #ifdef __cplusplus
 }

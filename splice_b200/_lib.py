@@ -71,6 +71,7 @@ class SpliceVitForwardArgs(C.Structure):
         ("n_grad", c_int), ("slot", c_int),
         ("keys32", c_void_p), ("cls32", c_void_p), ("qkv32_all", c_void_p), ("block32_all", c_void_p),
         ("gemm_impl", c_int),
+        ("pre_normalized", c_int),
     ]
 
 
@@ -105,9 +106,11 @@ splice_attention_bwd = _sig("splice_attention_bwd", c_int,
                             [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
 splice_resized_hw = _sig("splice_resized_hw", None, [c_int, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)])
 splice_preprocess_fwd = _sig("splice_preprocess_fwd", c_int,
-                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p])
+                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p])
+splice_resize_normalize = _sig("splice_resize_normalize", c_int,
+                               [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p])
 splice_preprocess_bwd = _sig("splice_preprocess_bwd", c_int,
-                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+                             [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p])
 splice_vit_packed_floats = _sig("splice_vit_packed_floats", c_size_t, [C.POINTER(SpliceVitDesc)])
 splice_vit_create = _sig("splice_vit_create", c_int,
                          [C.POINTER(c_void_p), C.POINTER(SpliceVitDesc), c_void_p, c_size_t, c_void_p])
@@ -121,14 +124,19 @@ splice_loss_mse = _sig("splice_loss_mse", c_int,
 splice_keys_self_sim = _sig("splice_keys_self_sim", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p])
 splice_weighted_total = _sig("splice_weighted_total", c_int, [c_void_p, C.POINTER(c_float), c_int, c_void_p, c_void_p])
 
+splice_adam_step = _sig("splice_adam_step", c_int,
+                        [C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
+                         C.POINTER(c_int), c_int, c_int, c_float, c_float, c_float, c_float, c_void_p])
+
 # every symbol include/splice_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "splice_version", "splice_last_error", "splice_launch_count", "splice_launch_count_reset",
     "splice_gemm_bf16",
     "splice_layernorm_fwd", "splice_layernorm_bwd", "splice_attention_fwd", "splice_attention_bwd",
-    "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd",
+    "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd", "splice_resize_normalize",
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
+    "splice_adam_step",
 ]
 
 

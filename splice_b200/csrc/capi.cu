@@ -5,6 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <math.h>
+
+#include "adam.h"
 #include "attention.h"
 #include "common.cuh"
 #include "elementwise.h"
@@ -79,12 +82,16 @@ SPLICE_API void splice_resized_hw(int h, int w, int size, int max_size, int* oh,
     resized_hw(h, w, size, max_size, oh, ow);
 }
 SPLICE_API int splice_preprocess_fwd(const void* img, int h, int w, int oh, int ow, int patch, void* patches, int row0,
-                                     void* stream) {
-    return preprocess_fwd((const float*)img, h, w, oh, ow, patch, (bf16*)patches, row0, (cudaStream_t)stream);
+                                     int normalize, void* stream) {
+    return preprocess_fwd((const float*)img, h, w, oh, ow, patch, (bf16*)patches, row0, normalize != 0, (cudaStream_t)stream);
+}
+SPLICE_API int splice_resize_normalize(const void* img, int h, int w, int oh, int ow, void* out, int normalize, void* stream) {
+    return resize_normalize((const float*)img, h, w, oh, ow, (float*)out, normalize != 0, (cudaStream_t)stream);
 }
 SPLICE_API int splice_preprocess_bwd(const void* dpatch, int ldp, int row0, int h, int w, int oh, int ow, int patch,
-                                     void* dimg, void* stream) {
-    return preprocess_bwd((const float*)dpatch, ldp, row0, h, w, oh, ow, patch, (float*)dimg, (cudaStream_t)stream);
+                                     void* dimg, int normalize, void* stream) {
+    return preprocess_bwd((const float*)dpatch, ldp, row0, h, w, oh, ow, patch, (float*)dimg, normalize != 0,
+                          (cudaStream_t)stream);
 }
 
 // ---- ViT engine ----------------------------------------------------------------------------------
@@ -116,12 +123,13 @@ SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* a, void
     v.images = imgs; v.n_images = a->n_images; v.out_h = a->out_h; v.out_w = a->out_w; v.pos = (const float*)a->pos;
     v.n_grad = a->n_grad; v.slot = a->slot; v.keys32 = (float*)a->keys32; v.cls32 = (float*)a->cls32;
     v.qkv32_all = (float*)a->qkv32_all; v.block32_all = (float*)a->block32_all; v.gemm_impl = a->gemm_impl;
+    v.pre_normalized = a->pre_normalized != 0;
     return static_cast<VitEngine*>(ctx)->forward(v, (cudaStream_t)stream);
 }
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, void* stream) {
     SPLICE_REQUIRE(ctx && a && a->grads, "splice_vit_backward: null argument");
     VitEngine* e = static_cast<VitEngine*>(ctx);
-    SPLICE_REQUIRE(a->slot == 0 || a->slot == 1, "splice_vit_backward: slot must be 0 or 1");
+    SPLICE_REQUIRE(a->slot >= 0 && a->slot < 4, "splice_vit_backward: slot must be in [0,4)");
     const int n = e->slot_n_grad(a->slot);
     SPLICE_REQUIRE(n > 0 && n <= 64, "splice_vit_backward: slot %d holds no forward pass with n_grad > 0", a->slot);
     ImageGradRef g[64];
@@ -221,6 +229,33 @@ SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows
 
 SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream) {
     return weighted_total((const float*)terms, weights_host, n, (float*)total, (cudaStream_t)stream);
+}
+
+// ---- optimiser -----------------------------------------------------------------------------------
+SPLICE_API int splice_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                                const int* numel, int n_tensors, int step, float lr, float beta1, float beta2, float eps,
+                                void* stream) {
+    SPLICE_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && n_tensors > 0 && step >= 1, "splice_adam_step: bad argument");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float lr_over_bc1 = (float)((double)lr / bc1);
+    const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    for (int i0 = 0; i0 < n_tensors; i0 += ADAM_MAX_TENSORS) {
+        AdamTable tab;
+        const int cnt = (n_tensors - i0 < ADAM_MAX_TENSORS) ? n_tensors - i0 : ADAM_MAX_TENSORS;
+        int max_n = 0;
+        for (int i = 0; i < cnt; ++i) {
+            tab.p[i] = (float*)params[i0 + i]; tab.g[i] = (const float*)grads[i0 + i];
+            tab.m[i] = (float*)exp_avg[i0 + i]; tab.v[i] = (float*)exp_avg_sq[i0 + i];
+            tab.n[i] = numel[i0 + i];
+            SPLICE_REQUIRE(tab.p[i] && tab.g[i] && tab.m[i] && tab.v[i] && tab.n[i] > 0, "splice_adam_step: null tensor %d", i0 + i);
+            if (tab.n[i] > max_n) max_n = tab.n[i];
+        }
+        for (int i = cnt; i < ADAM_MAX_TENSORS; ++i) { tab.p[i] = nullptr; tab.g[i] = nullptr; tab.m[i] = nullptr; tab.v[i] = nullptr; tab.n[i] = 0; }
+        int rc = adam_step(tab, cnt, max_n, lr_over_bc1, inv_bc2_sqrt, beta1, beta2, eps, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return SPLICE_OK;
 }
 
 }  // extern "C"

@@ -121,7 +121,38 @@ __constant__ float c_istd[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const float* __restrict__ img, int h, int w, int oh, int ow,
                                                              const int* __restrict__ ys, const float* __restrict__ wy, int ty,
                                                              const int* __restrict__ xs, const float* __restrict__ wx, int tx,
-                                                             int patch, bf16* __restrict__ patches, int row0) {
+                                                             int patch, bf16* __restrict__ patches, int row0, bool normalize) {
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int c = blockIdx.z;
+    // the patch conv (k = stride = patch, no padding) ignores the trailing oh % patch rows / ow % patch columns
+    if (i >= (oh / patch) * patch || j >= (ow / patch) * patch) return;
+    const float* src = img + (size_t)c * h * w;
+    const int y0 = ys[i], x0 = xs[j];
+    float acc = 0.f;
+    for (int u = 0; u < ty; ++u) {
+        const float a = wy[i * ty + u];
+        if (a == 0.f) continue;
+        const float* r = src + (size_t)(y0 + u) * w + x0;
+        float racc = 0.f;
+        for (int v = 0; v < tx; ++v) {
+            const float b = wx[j * tx + v];
+            if (b != 0.f) racc = fmaf(b, r[v], racc);
+        }
+        acc = fmaf(a, racc, acc);
+    }
+    const float val = normalize ? (acc - c_mean[c]) * c_istd[c] : acc;
+    const int gw = ow / patch;
+    const int row = row0 + (i / patch) * gw + (j / patch);
+    const int col = c * patch * patch + (i % patch) * patch + (j % patch);
+    patches[(size_t)row * (3 * patch * patch) + col] = __float2bfloat16(val);
+}
+
+// plain image output [3, oh, ow] (the standalone LossG.global_transform of the reference API)
+__global__ void __launch_bounds__(256) resize_normalize_kernel(const float* __restrict__ img, int h, int w, int oh, int ow,
+                                                               const int* __restrict__ ys, const float* __restrict__ wy, int ty,
+                                                               const int* __restrict__ xs, const float* __restrict__ wx, int tx,
+                                                               float* __restrict__ out, bool normalize) {
     const int j = blockIdx.x * 32 + (threadIdx.x & 31);
     const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int c = blockIdx.z;
@@ -140,64 +171,74 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const float* __rest
         }
         acc = fmaf(a, racc, acc);
     }
-    const float val = (acc - c_mean[c]) * c_istd[c];
-    const int gw = ow / patch;
-    const int row = row0 + (i / patch) * gw + (j / patch);
-    const int col = c * patch * patch + (i % patch) * patch + (j % patch);
-    patches[(size_t)row * (3 * patch * patch) + col] = __float2bfloat16(val);
+    out[((size_t)c * oh + i) * ow + j] = normalize ? (acc - c_mean[c]) * c_istd[c] : acc;
 }
 
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const float* __restrict__ dpatch, int ldp, int row0, int h, int w,
                                                              int oh, int ow, const int* __restrict__ ys, const float* __restrict__ wy,
                                                              int ty, const int* __restrict__ xs, const float* __restrict__ wx, int tx,
-                                                             int patch, float* __restrict__ dimg) {
+                                                             int patch, float* __restrict__ dimg, bool normalize) {
     const int b = blockIdx.x * 32 + (threadIdx.x & 31);
     const int a = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int c = blockIdx.z;
     if (a >= h || b >= w) return;
     const int i0 = ys[a], j0 = xs[b];
     const int gw = ow / patch, pp = patch * patch;
+    const int ch = (oh / patch) * patch, cw = gw * patch;  // region covered by whole patches
     float acc = 0.f;
     for (int u = 0; u < ty; ++u) {
         const float wa = wy[a * ty + u];
         const int i = i0 + u;
-        if (wa == 0.f || i >= oh) continue;
+        if (wa == 0.f || i >= ch) continue;
         float racc = 0.f;
         for (int v = 0; v < tx; ++v) {
             const float wb = wx[b * tx + v];
             const int j = j0 + v;
-            if (wb == 0.f || j >= ow) continue;
+            if (wb == 0.f || j >= cw) continue;
             const int row = row0 + (i / patch) * gw + (j / patch);
             const int col = c * pp + (i % patch) * patch + (j % patch);
             racc = fmaf(wb, dpatch[(size_t)row * ldp + col], racc);
         }
         acc = fmaf(wa, racc, acc);
     }
-    dimg[((size_t)c * h + a) * w + b] = acc * c_istd[c];
+    dimg[((size_t)c * h + a) * w + b] = normalize ? acc * c_istd[c] : acc;
 }
 
-int preprocess_fwd(const float* img, int h, int w, int oh, int ow, int patch, bf16* patches, int row0, cudaStream_t stream) {
+int preprocess_fwd(const float* img, int h, int w, int oh, int ow, int patch, bf16* patches, int row0, bool normalize,
+                   cudaStream_t stream) {
     SPLICE_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0, "preprocess: empty image");
-    SPLICE_REQUIRE(oh % patch == 0 && ow % patch == 0, "preprocess: %dx%d is not a multiple of the patch size %d", oh, ow, patch);
+    SPLICE_REQUIRE(oh >= patch && ow >= patch, "preprocess: %dx%d is smaller than one %d-pixel patch", oh, ow, patch);
     TablePair ty, tx;
     int rc = get_tables(h, oh, &ty); if (rc) return rc;
     rc = get_tables(w, ow, &tx); if (rc) return rc;
     dim3 grid(ceil_div(ow, 32), ceil_div(oh, 8), 3);
     preprocess_fwd_kernel<<<grid, 256, 0, stream>>>(img, h, w, oh, ow, ty.fwd.start, ty.fwd.w, ty.fwd.taps, tx.fwd.start, tx.fwd.w,
-                                                    tx.fwd.taps, patch, patches, row0);
+                                                    tx.fwd.taps, patch, patches, row0, normalize);
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
+int resize_normalize(const float* img, int h, int w, int oh, int ow, float* out, bool normalize, cudaStream_t stream) {
+    SPLICE_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0, "resize_normalize: empty image");
+    TablePair ty, tx;
+    int rc = get_tables(h, oh, &ty); if (rc) return rc;
+    rc = get_tables(w, ow, &tx); if (rc) return rc;
+    dim3 grid(ceil_div(ow, 32), ceil_div(oh, 8), 3);
+    resize_normalize_kernel<<<grid, 256, 0, stream>>>(img, h, w, oh, ow, ty.fwd.start, ty.fwd.w, ty.fwd.taps, tx.fwd.start,
+                                                      tx.fwd.w, tx.fwd.taps, out, normalize);
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
 
 int preprocess_bwd(const float* dpatch, int ldp, int row0, int h, int w, int oh, int ow, int patch, float* dimg,
-                   cudaStream_t stream) {
-    SPLICE_REQUIRE(oh % patch == 0 && ow % patch == 0, "preprocess_bwd: %dx%d is not a multiple of the patch size %d", oh, ow, patch);
+                   bool normalize, cudaStream_t stream) {
+    SPLICE_REQUIRE(oh >= patch && ow >= patch, "preprocess_bwd: %dx%d is smaller than one %d-pixel patch", oh, ow, patch);
     TablePair ty, tx;
     int rc = get_tables(h, oh, &ty); if (rc) return rc;
     rc = get_tables(w, ow, &tx); if (rc) return rc;
     dim3 grid(ceil_div(w, 32), ceil_div(h, 8), 3);
     preprocess_bwd_kernel<<<grid, 256, 0, stream>>>(dpatch, ldp, row0, h, w, oh, ow, ty.bwd.start, ty.bwd.w, ty.bwd.taps,
-                                                    tx.bwd.start, tx.bwd.w, tx.bwd.taps, patch, dimg);
+                                                    tx.bwd.start, tx.bwd.w, tx.bwd.taps, patch, dimg, normalize);
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

@@ -212,22 +212,23 @@ int VitEngine::configure(Slot& s, int S, int t, int n_grad) {
 
 int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
     SPLICE_REQUIRE(a.images && a.n_images > 0, "vit_forward: no images");
-    SPLICE_REQUIRE(a.slot == 0 || a.slot == 1, "vit_forward: slot must be 0 or 1");
+    SPLICE_REQUIRE(a.slot >= 0 && a.slot < 4, "vit_forward: slot must be in [0,4)");
     SPLICE_REQUIRE(a.n_grad >= 0 && a.n_grad <= a.n_images, "vit_forward: n_grad out of range");
     const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
-    SPLICE_REQUIRE(a.out_h > 0 && a.out_w > 0 && a.out_h % p == 0 && a.out_w % p == 0,
-                   "vit_forward: ViT input %dx%d must be a positive multiple of the patch size %d", a.out_h, a.out_w, p);
+    SPLICE_REQUIRE(a.out_h >= p && a.out_w >= p, "vit_forward: ViT input %dx%d is smaller than one %d-pixel patch", a.out_h,
+                   a.out_w, p);
     const int gh = a.out_h / p, gw = a.out_w / p, t = 1 + gh * gw, S = a.n_images, M = S * t;
     SPLICE_REQUIRE(a.pos || (t == d_.n_pos && gh == gw),
                    "vit_forward: token grid %dx%d differs from the trained grid; pass an interpolated pos_embed", gh, gw);
     Slot& s = slots_[a.slot];
     RC(configure(s, S, t, a.n_grad));
-    s.gh = gh; s.gw = gw; s.oh = a.out_h; s.ow = a.out_w;
+    s.gh = gh; s.gw = gw; s.oh = a.out_h; s.ow = a.out_w; s.pre_normalized = a.pre_normalized;
     s.imgs.assign(a.images, a.images + S);
     const float* pos = a.pos ? a.pos : pos_;
 
     for (int i = 0; i < S; ++i)
-        RC(preprocess_fwd(a.images[i].data, a.images[i].h, a.images[i].w, a.out_h, a.out_w, p, s.patches, i * (t - 1), stream));
+        RC(preprocess_fwd(a.images[i].data, a.images[i].h, a.images[i].w, a.out_h, a.out_w, p, s.patches, i * (t - 1),
+                          !a.pre_normalized, stream));
     RC(write_cls_rows(s.x0[0], cls_, pos, S, t, D, stream));
     {
         GemmEpilogue ep;
@@ -274,7 +275,7 @@ int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
 }
 
 int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
-    SPLICE_REQUIRE(a.slot == 0 || a.slot == 1, "vit_backward: slot must be 0 or 1");
+    SPLICE_REQUIRE(a.slot >= 0 && a.slot < 4, "vit_backward: slot must be in [0,4)");
     Slot& s = slots_[a.slot];
     SPLICE_REQUIRE(s.pool && s.n_grad > 0, "vit_backward: slot %d holds no forward pass with n_grad > 0", a.slot);
     SPLICE_REQUIRE(a.grads, "vit_backward: no gradient outputs");
@@ -333,7 +334,8 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
                        "vit_backward: gradient %d is %dx%d but the forward image was %dx%d", i, a.grads[i].h, a.grads[i].w,
                        s.imgs[i].h, s.imgs[i].w);
         if (!a.grads[i].data) continue;
-        RC(preprocess_bwd(s.dpatch, pp3, i * t + 1, s.imgs[i].h, s.imgs[i].w, s.oh, s.ow, p, a.grads[i].data, stream));
+        RC(preprocess_bwd(s.dpatch, pp3, i * t + 1, s.imgs[i].h, s.imgs[i].w, s.oh, s.ow, p, a.grads[i].data,
+                          !s.pre_normalized, stream));
     }
     return SPLICE_OK;
 }

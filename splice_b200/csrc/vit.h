@@ -26,6 +26,7 @@ struct VitForwardArgs {
     float* qkv32_all = nullptr;       // [depth, n_images*t, 3D]   (compat taps)
     float* block32_all = nullptr;     // [depth, n_images*t, D]    (compat taps)
     int gemm_impl = 0;                // 0 = tcgen05, 1 = SIMT cross-check
+    bool pre_normalized = false;
 };
 
 struct VitBackwardArgs {
@@ -55,7 +56,7 @@ private:
     };
     struct Slot {
         int S = 0, t = 0, gh = 0, gw = 0, n_grad = 0, oh = 0, ow = 0;
-        bool pos_custom = false;
+        bool pos_custom = false, pre_normalized = false;
         std::vector<ImageRef> imgs;
         void* pool = nullptr;
         size_t pool_bytes = 0;
@@ -77,7 +78,7 @@ private:
     const float *cls_ = nullptr, *pos_ = nullptr, *pe_b_ = nullptr, *norm_g_ = nullptr, *norm_b_ = nullptr;
     const bf16 *pe_w_ = nullptr, *pe_wT_ = nullptr;
     std::vector<LayerW> L_;
-    Slot slots_[2];
+    Slot slots_[4];
     void* loss_ws_ = nullptr;
     size_t loss_ws_bytes_ = 0;
 };

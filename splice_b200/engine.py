@@ -117,13 +117,11 @@ class VitEngine:
     # ---- forward / backward ------------------------------------------------------------------------
     def forward(self, images: Sequence[torch.Tensor], out_hw: Tuple[int, int], n_grad: int = 0, slot: int = 0,
                 want_keys: bool = True, want_cls: bool = True, want_all_qkv: bool = False,
-                want_all_blocks: bool = False) -> Dict[str, torch.Tensor]:
+                want_all_blocks: bool = False, pre_normalized: bool = False) -> Dict[str, torch.Tensor]:
         """images: fp32 CUDA tensors [3,h,w] in [0,1] (sizes may differ); all are resized to out_hw.
         Returns {'keys': [S,t,D], 'cls': [S,D], 'qkv': [12,S,t,3D], 'block': [12,S,t,D]} (only the requested)."""
         S = len(images)
         oh, ow = out_hw
-        if oh % self.patch or ow % self.patch:
-            raise ValueError(f"ViT input {oh}x{ow} is not a multiple of the patch size {self.patch}")
         t = self.tokens(oh, ow)
         arr = (_lib.SpliceImage * S)()
         keep = []
@@ -153,9 +151,14 @@ class VitEngine:
         a.keys32, a.cls32 = ptr(out.get("keys")), ptr(out.get("cls"))
         a.qkv32_all, a.block32_all = ptr(out.get("qkv")), ptr(out.get("block"))
         a.gemm_impl = self.gemm_impl
+        a.pre_normalized = 1 if pre_normalized else 0
         check(_lib.splice_vit_forward(self._ctx, C.byref(a), cur_stream()), "splice_vit_forward")
         self._slot_meta[slot] = {"shapes": [(im.shape[1], im.shape[2]) for im in keep[:n_grad]], "t": t, "keep": keep}
         return out
+
+    def forward_normalized(self, img: torch.Tensor, **want) -> Dict[str, torch.Tensor]:
+        """One already-normalised [3,h,w] image at ViT resolution (the VitExtractor API contract)."""
+        return self.forward([img], (img.shape[1], img.shape[2]), n_grad=0, slot=3, pre_normalized=True, **want)
 
     def backward(self, slot: int, dkeys: Optional[torch.Tensor], dcls: Optional[torch.Tensor]) -> List[torch.Tensor]:
         """d(loss)/d(image) for the first n_grad images of the forward held in `slot`."""

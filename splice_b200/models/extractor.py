@@ -1,0 +1,155 @@
+"""Drop-in for the reference's `models/extractor.py` (VitExtractor + attn_cosine_sim), backed by the
+sm_100a ViT engine instead of a hooked torch module.
+
+Same public names, argument orders and return shapes as /root/reference/models/extractor.py:4-163. The
+reference registers 48 forward hooks per call and returns *lists of all 12 layers'* tensors; the engine
+computes those taps directly (fp32 exports of the qkv GEMM / residual stream). The fused loss path
+(util/losses.py) does not go through these list-returning methods.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from ..engine import DINO_ARCH, VitEngine
+
+
+def attn_cosine_sim(x, eps=1e-08):
+    """ref extractor.py:4-9 — x [1,1,t,D] -> [1,t,t]. Runs on the engine's Gram kernels when an engine is
+    alive on x's device with matching D, otherwise raises (no CPU fallback)."""
+    x = x[0]
+    eng = VitExtractor._engine_for(x)
+    if eng is None:
+        raise RuntimeError("attn_cosine_sim needs a VitExtractor (engine) on a CUDA device with matching width")
+    return eng.keys_self_sim(x[0].detach().float().contiguous())[None]
+
+
+class VitExtractor:
+    BLOCK_KEY = 'block'
+    ATTN_KEY = 'attn'
+    PATCH_IMD_KEY = 'patch_imd'
+    QKV_KEY = 'qkv'
+    KEY_LIST = [BLOCK_KEY, ATTN_KEY, PATCH_IMD_KEY, QKV_KEY]
+
+    _engines: List[VitEngine] = []
+
+    def __init__(self, model_name, device, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        """ref extractor.py:19-29. `state_dict` (optional, extension): DINO weights to use instead of
+        `torch.hub.load('facebookresearch/dino:main', model_name)`; with SPLICE_B200_RANDOM_DINO=1 a seeded
+        random DINO-style init is used when the hub is unreachable (benchmarks / offline tests)."""
+        if model_name not in DINO_ARCH:
+            raise NotImplementedError(f"model {model_name!r} is not a DINO ViT supported by splice_b200")
+        self.model_name = model_name
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("splice_b200.VitExtractor runs on sm_100a only; there is no CPU fallback")
+        self.model = None
+        if state_dict is None:
+            if os.environ.get("SPLICE_B200_RANDOM_DINO", "0") == "1":
+                from ..dino_init import random_dino_state_dict
+
+                state_dict = random_dino_state_dict(model_name)
+            else:
+                self.model = torch.hub.load('facebookresearch/dino:main', model_name).to(device)
+                self.model.eval()
+                state_dict = self.model.state_dict()
+        self.engine = VitEngine(model_name, state_dict, self.device)
+        VitExtractor._engines.append(self.engine)
+        self.hook_handlers = []
+        self.layers_dict = {key: list(range(12)) for key in VitExtractor.KEY_LIST}
+        self.outputs_dict = {key: [] for key in VitExtractor.KEY_LIST}
+
+    @classmethod
+    def _engine_for(cls, x: torch.Tensor) -> Optional[VitEngine]:
+        for e in reversed(cls._engines):
+            if e.device == x.device and e.dim == x.shape[-1]:
+                return e
+        return None
+
+    # ---- taps (ref extractor.py:81-103) ------------------------------------------------------------
+    def _run(self, input_img, **want):
+        if input_img.dim() != 4 or input_img.shape[0] != 1:
+            raise ValueError("VitExtractor expects a [1,3,h,w] batch (ref extractor.py:143 requires batch 1)")
+        _, _, h, w = input_img.shape
+        return self.engine.forward_normalized(input_img[0], **want)
+
+    def get_feature_from_input(self, input_img):  # List([B, N, D])
+        res = self._run(input_img, want_all_blocks=True)
+        return [res["block"][i] for i in range(12)]
+
+    def get_qkv_feature_from_input(self, input_img):
+        res = self._run(input_img, want_all_qkv=True)
+        return [res["qkv"][i] for i in range(12)]
+
+    def get_attn_feature_from_input(self, input_img):
+        """Materialising compatibility path: post-softmax probabilities [1,H,t,t] per layer (ref :97-103).
+        Not used by the optimisation loop (the fused attention kernel never forms them)."""
+        res = self._run(input_img, want_all_qkv=True)
+        out = []
+        H = self.get_head_num()
+        for i in range(12):
+            qkv = res["qkv"][i]
+            t = qkv.shape[1]
+            q, k, _ = qkv.reshape(1, t, 3, H, -1).permute(2, 0, 3, 1, 4)
+            out.append(((q @ k.transpose(-2, -1)) * q.shape[-1] ** -0.5).softmax(dim=-1))
+        return out
+
+    # ---- shape helpers (ref extractor.py:105-130) ---------------------------------------------------
+    def get_patch_size(self):
+        return 8 if "8" in self.model_name else 16
+
+    def get_width_patch_num(self, input_img_shape):
+        b, c, h, w = input_img_shape
+        return w // self.get_patch_size()
+
+    def get_height_patch_num(self, input_img_shape):
+        b, c, h, w = input_img_shape
+        return h // self.get_patch_size()
+
+    def get_patch_num(self, input_img_shape):
+        return 1 + self.get_height_patch_num(input_img_shape) * self.get_width_patch_num(input_img_shape)
+
+    def get_head_num(self):
+        if "dino" in self.model_name:
+            return 6 if "s" in self.model_name else 12
+        return 6 if "small" in self.model_name else 12
+
+    def get_embedding_dim(self):
+        if "dino" in self.model_name:
+            return 384 if "s" in self.model_name else 768
+        return 384 if "small" in self.model_name else 768
+
+    # ---- q/k/v slicing (ref extractor.py:132-151) ---------------------------------------------------
+    def _split_qkv(self, qkv, input_img_shape, which):
+        t = self.get_patch_num(input_img_shape)
+        H = self.get_head_num()
+        D = self.get_embedding_dim()
+        return qkv.reshape(t, 3, H, D // H).permute(1, 2, 0, 3)[which]
+
+    def get_queries_from_qkv(self, qkv, input_img_shape):
+        return self._split_qkv(qkv, input_img_shape, 0)
+
+    def get_keys_from_qkv(self, qkv, input_img_shape):
+        return self._split_qkv(qkv, input_img_shape, 1)
+
+    def get_values_from_qkv(self, qkv, input_img_shape):
+        return self._split_qkv(qkv, input_img_shape, 2)
+
+    def get_keys_from_input(self, input_img, layer_num):
+        """[H,t,dh] keys of `layer_num` (ref :153-156). Layer 11 is served by the engine's direct fp32 export."""
+        if layer_num in (11, -1):
+            res = self._run(input_img)
+            t = res["keys"].shape[1]
+            H = self.get_head_num()
+            return res["keys"][0].reshape(t, H, -1).permute(1, 0, 2)
+        qkv_features = self.get_qkv_feature_from_input(input_img)[layer_num]
+        return self.get_keys_from_qkv(qkv_features, input_img.shape)
+
+    def get_keys_self_sim_from_input(self, input_img, layer_num):
+        """[1,t,t] cosine self-similarity of the concatenated keys (ref :158-163)."""
+        keys = self.get_keys_from_input(input_img, layer_num=layer_num)
+        h, t, d = keys.shape
+        concatenated_keys = keys.transpose(0, 1).reshape(t, h * d).contiguous()
+        return self.engine.keys_self_sim(concatenated_keys)[None]

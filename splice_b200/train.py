@@ -1,0 +1,82 @@
+"""Optimisation loop (drop-in for the reference's train.py:15-89): `train_model(dataroot, callback=None)` and
+the `python -m splice_b200.train --dataroot ...` CLI. Same sequence of calls as the reference loop; the
+config is looked up at the reference's cwd-relative path first, then at the packaged copy.
+"""
+from __future__ import annotations
+
+import os
+import random
+from argparse import ArgumentParser
+from pathlib import Path
+
+import numpy as np
+import torch
+import yaml
+from tqdm import tqdm
+
+from .data.Dataset import SingleImageDataset
+from .models.model import Model
+from .util.losses import LossG
+from .util.util import get_optimizer, get_scheduler, save_result
+
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+def load_config(overrides=None):
+    path = Path("conf/default/config.yaml")
+    if not path.exists():
+        path = Path(__file__).resolve().parent / "conf" / "default" / "config.yaml"
+    with open(path, "r") as f:
+        cfg = yaml.safe_load(f)
+    cfg.update(overrides or {})
+    return cfg
+
+
+def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
+    cfg = load_config(overrides)
+    if dataroot is not None:
+        cfg['dataroot'] = dataroot
+    seed = cfg['seed']
+    if seed == -1:
+        seed = np.random.randint(2 ** 32 - 1, dtype=np.int64)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    print(f'running with seed: {seed}.')
+
+    dataset = SingleImageDataset(cfg)
+    model = Model(cfg)
+    criterion = LossG(cfg, state_dict=vit_state_dict)
+    optimizer = get_optimizer(cfg, model.netG.parameters())
+    scheduler = get_scheduler(optimizer, lr_policy=cfg['scheduler_policy'], n_epochs=cfg['n_epochs'],
+                              n_epochs_decay=cfg['scheduler_n_epochs_decay'],
+                              lr_decay_iters=cfg['scheduler_lr_decay_iters'])
+
+    with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
+        for epoch in tepoch:
+            inputs = {k: v.to(device) for k, v in dataset[0].items()}
+            optimizer.zero_grad()
+            outputs = model(inputs)
+            losses = criterion(outputs, inputs)
+            loss_G = losses['loss']
+            lr = optimizer.param_groups[0]['lr']
+            tepoch.set_description(f"Epoch {epoch}")
+            tepoch.set_postfix(loss=loss_G.item(), lr=lr)
+
+            if epoch % cfg['log_images_freq'] == 0:
+                with torch.no_grad():
+                    output = model.netG(dataset.get_A().to(device))
+                save_result(output[0], cfg['dataroot'])
+                if callback is not None:
+                    callback(output[0])
+
+            loss_G.backward()
+            optimizer.step()
+            scheduler.step()
+    return model
+
+
+if __name__ == '__main__':
+    parser = ArgumentParser()
+    parser.add_argument("--dataroot", type=str)
+    train_model(parser.parse_args().dataroot)

@@ -296,21 +296,17 @@ def preprocess_fwd_bwd():
         g = torch.Generator(device="cuda").manual_seed(h * 1000 + w)
         img = torch.rand(3, h, w, device="cuda", generator=g)
         oh, ow = R.resized_hw(h, w, size, 480)
-        oh_p, ow_p = oh - oh % patch, ow - ow % patch  # the engine only accepts multiples of the patch
-        if (oh_p, ow_p) != (oh, ow):
-            out.append({"h": h, "w": w, "skip": "not patch-aligned", "ok": True})
-            continue
         gh, gw = oh // patch, ow // patch
         pp3 = 3 * patch * patch
         patches = torch.zeros(gh * gw, pp3, device="cuda", dtype=torch.bfloat16)
-        ck(_lib.splice_preprocess_fwd(ptr(img), h, w, oh, ow, patch, ptr(patches), 0, cur_stream()))
+        ck(_lib.splice_preprocess_fwd(ptr(img), h, w, oh, ow, patch, ptr(patches), 0, 1, cur_stream()))
         x = img.clone().requires_grad_(True)
         tr = R.global_transform(x, size)
-        ref = torch.nn.functional.unfold(tr[None], patch, stride=patch)[0].t()  # [gh*gw, 3*p*p]
+        ref = torch.nn.functional.unfold(tr[None], patch, stride=patch)[0].t()  # [gh*gw, 3*p*p]; drops the remainder
         dp = torch.randn(gh * gw, pp3, device="cuda", generator=g)
         ref.backward(dp)
         dimg = torch.full((3, h, w), float("nan"), device="cuda")
-        ck(_lib.splice_preprocess_bwd(ptr(dp), pp3, 0, h, w, oh, ow, patch, ptr(dimg), cur_stream()))
+        ck(_lib.splice_preprocess_bwd(ptr(dp), pp3, 0, h, w, oh, ow, patch, ptr(dimg), 1, cur_stream()))
         torch.cuda.synchronize()
         r = {"h": h, "w": w, "oh": oh, "ow": ow, "fwd_maxabs": _maxabs(patches, ref), "bwd_rel": _rel(dimg, x.grad)}
         r["ok"] = r["fwd_maxabs"] < 2e-2 and r["bwd_rel"] < 1e-5
@@ -372,7 +368,7 @@ def vit_forward_b8():
 
 @check
 def vit_forward_nonsquare():
-    return _vit_forward_case("dino_vits16", [(225, 300)], (224, 298 - 298 % 16))
+    return _vit_forward_case("dino_vits16", [(225, 300)], (224, 298)) + _vit_forward_case("dino_vitb8", [(225, 300)], (224, 298))
 
 
 @check
@@ -461,6 +457,138 @@ def vit_loss_backward_s16_simt():
 @check
 def vit_loss_backward_b8():
     return _vit_loss_backward_case("dino_vitb8", 224, 217)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-facing classes: teacher-forced steps against the golden fixtures made from the reference itself
+# ------------------------------------------------------------------------------------------------
+def _sample(t, summ):
+    return t.detach().reshape(-1).double().cpu()[summ["idx"]].float()
+
+
+@check
+def train_step_golden():
+    import torch
+
+    dino_vit, R = _oracle_on_gpu()
+    from splice_b200.models.model import Model
+    from splice_b200.util.losses import LossG
+    from splice_b200.util.util import get_optimizer
+
+    gold = torch.load(ROOT / "tests" / "golden" / "step_s16.pt")
+    cfg = gold["cfg"]
+    vsd = {k: v.detach() for k, v in dino_vit.build("dino_vits16").state_dict().items()}
+    model = Model(cfg)
+    crit = LossG(cfg, state_dict=vsd)
+    out = []
+    for step in (0, 1, 75):
+        rec = gold["steps"][step]
+        model.netG.load_state_dict(gold["netG"])
+        inputs = {k: v.cuda() for k, v in rec["inputs"].items()}
+        outputs = model(inputs)
+        for v in outputs.values():
+            v.retain_grad()
+        for p in model.netG.parameters():
+            p.grad = None
+        losses = crit(outputs, inputs)
+        losses["loss"].backward()
+        torch.cuda.synchronize()
+        r = {"step": step}
+        worst = 0.0
+        for k, v in rec["losses"].items():
+            e = abs(float(losses[k]) - v) / max(abs(v), 1e-12)
+            r[k] = float(losses[k]); r[k + "_ref"] = v
+            worst = max(worst, e)
+        r["loss_rel"] = worst
+        gx = outputs["x_global"].grad
+        r["dx_rel"] = _rel(gx.cpu(), rec["dout_x_global"])
+        gw = {k: p.grad for k, p in model.netG.named_parameters()}
+        # netG gradient summaries: relative error of the sampled entries, weights only (conv biases that feed a
+        # BatchNorm have a true gradient of zero: both sides hold rounding noise there, SURVEY.md hard part 1)
+        errs = []
+        for k, summ in rec["grads"].items():
+            if k.endswith(".bias") and not k.startswith("9."):
+                parent = k[:-len(".bias")]
+                if parent.endswith(".0"):
+                    continue
+            a, b = _sample(gw[k], summ), summ["samples"]
+            errs.append(((a - b).norm() / b.norm().clamp_min(1e-20)).item())
+        r["netG_grad_rel_max"] = max(errs)
+        r["netG_grad_rel_med"] = sorted(errs)[len(errs) // 2]
+        r["ok"] = r["loss_rel"] < 5e-3 and r["dx_rel"] < 2e-2 and r["netG_grad_rel_med"] < 2e-2
+        if step == 1:
+            opt = get_optimizer(cfg, model.netG.parameters())
+            opt.step()
+            torch.cuda.synchronize()
+            perr = []
+            for k, p in model.netG.named_parameters():
+                if k.endswith(".bias") and k[:-5].endswith(".0") and not k.startswith("9."):
+                    continue
+                a, b = _sample(p, rec["post_adam"][k]), rec["post_adam"][k]["samples"]
+                perr.append((a - b).abs().max().item())
+            # beta1 = 0 makes the first Adam step a sign step of size lr: entries whose gradient sign flips under
+            # bf16 rounding move by 2*lr; report the fraction instead of a norm
+            r["post_adam_maxabs"] = max(perr)
+            r["ok"] = r["ok"] and r["post_adam_maxabs"] <= 2 * cfg["lr"] * 1.01
+        out.append(r)
+    return out
+
+
+@check
+def adam_kernel():
+    import torch
+    from splice_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    shapes = [(128, 132, 3, 3), (16,), (3, 16, 1, 1), (1,), (4, 3, 1, 1)] * 30
+    ps = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    a = FusedAdam(ps, lr=2e-3, betas=(0.0, 0.99))
+    b = torch.optim.Adam(qs, lr=2e-3, betas=(0.0, 0.99))
+    worst = 0.0
+    for it in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p) * (10.0 ** (it - 3))
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step(); b.step()
+        worst = max(worst, max((p - q).abs().max().item() for p, q in zip(ps, qs)))
+    a2 = FusedAdam([ps[0]], lr=1e-3, betas=(0.9, 0.999))
+    b2 = torch.optim.Adam([qs[0]], lr=1e-3, betas=(0.9, 0.999))
+    for it in range(3):
+        g = torch.randn_like(ps[0]); ps[0].grad, qs[0].grad = g.clone(), g.clone()
+        a2.step(); b2.step()
+    w2 = (ps[0] - qs[0]).abs().max().item()
+    sd = a.state_dict()
+    ok_sd = all(float(st["step"]) == 5.0 for st in sd["state"].values())
+    return [{"max_abs_vs_torch": worst, "general_betas": w2, "state_dict_steps": ok_sd, "ok": worst < 2e-6 and w2 < 2e-6 and ok_sd}]
+
+
+@check
+def train_loop_smoke():
+    """train_model on a synthetic pair for a few steps (incl. an image-logging step); loss must stay finite."""
+    import tempfile
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from splice_b200.train import train_model
+
+    root = Path(tempfile.mkdtemp())
+    for sub, seed, grid in (("A", 1000, 8), ("B", 1001, 16)):
+        (root / sub).mkdir()
+        rng = np.random.default_rng(seed)
+        low = rng.integers(0, 256, (grid, grid, 3), dtype=np.uint8)
+        img = np.asarray(Image.fromarray(low).resize((128, 128), Image.BICUBIC)).astype(np.float64)
+        img = np.clip(img + rng.normal(0, 8, img.shape), 0, 255).astype(np.uint8)
+        Image.fromarray(img).save(root / sub / "im.png")
+    os.environ["SPLICE_B200_RANDOM_DINO"] = "1"
+    seen = []
+    model = train_model(str(root), callback=lambda im: seen.append(tuple(im.shape)),
+                        overrides={"dino_model_name": "dino_vits16", "n_epochs": 12, "seed": 0})
+    torch.cuda.synchronize()
+    finite = all(torch.isfinite(p).all().item() for p in model.netG.parameters())
+    return [{"callbacks": seen, "png": (root / "out" / "output.png").exists(), "finite": finite,
+             "ok": finite and len(seen) == 1 and (root / "out" / "output.png").exists()}]
 
 
 # ------------------------------------------------------------------------------------------------
