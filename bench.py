@@ -1,0 +1,358 @@
+"""bench.py — optimisation-loop iterations/second per image pair (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # splice_b200 arm (N>1: under torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # reference arm: CPU oracle port
+
+A "step" is one iteration of the reference loop (train.py:53-80 without tqdm/PNG logging): netG on the
+structure and appearance crops, the DINO-ViT objective (key self-similarity + [CLS] + key identity, plus the
+"entire image" terms every 75th step), backward into netG, Adam. Workload at N=1: BASELINE.json configs[1]
+(224x224 pair, DINO ViT-B/8), synthetic pair per SURVEY.md §8d, seeded random DINO-style ViT weights (no
+network for checkpoints). With N GPUs every rank optimises its own pair (weak scaling, no data-path collective;
+one NCCL broadcast of the packed ViT weights at start-up).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "opt-loop iters/sec per image pair (DINO ViT-B/8, 224px)"
+UNIT = "it/s"
+VIT_GFLOP_PER_STEP = 983.2  # 4 forward + 2 dgrad-only backward ViT-B/8 sequences at t = 785
+
+
+def synth_image(seed: int, side: int, grid: int) -> torch.Tensor:
+    """SURVEY.md §8d synthetic pair recipe -> [3, side, side] float in [0,1]."""
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    low = rng.integers(0, 256, (grid, grid, 3), dtype=np.uint8)
+    img = np.asarray(Image.fromarray(low).resize((side, side), Image.BICUBIC)).astype(np.float64)
+    img = np.clip(img + rng.normal(0, 8, img.shape), 0, 255).astype(np.uint8)
+    return torch.from_numpy(img).permute(2, 0, 1).float() / 255.0
+
+
+def make_cfg(model_name: str) -> dict:
+    import yaml
+
+    cfg = yaml.safe_load(open(ROOT / "splice_b200" / "conf" / "default" / "config.yaml"))
+    cfg.update({"dino_model_name": model_name, "seed": 0})
+    return cfg
+
+
+def crop_schedule(A: torch.Tensor, B: torch.Tensor, n: int, seed: int, min_cover: float = 0.95):
+    """n (A_global, B_global) crop pairs with the reference's size law: side ~ U[0.95 h, h] rounded
+    (data/transforms.py:22-23), random position; augmentation colour ops do not change shapes and are skipped."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        pair = []
+        for img in (A, B):
+            h = img.shape[1]
+            s = int(round(rng.uniform(min_cover * h, h)))
+            y, x = rng.integers(0, h - s + 1), rng.integers(0, h - s + 1)
+            pair.append(img[None, :, y:y + s, x:x + s].contiguous())
+        out.append(tuple(pair))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001 - nvidia-smi missing: report no clocks rather than fail the bench
+            pass
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops": d.get("bf16_tflops_sustained", 1386.8), "hbm": d.get("hbm_gbs", 6553.9), "src": "measured (MEASURED_PEAKS.json, bf16 sustained)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(model_name: str, side: int, n_warm: int, n_steps: int, budget_s: float):
+    """Times full optimisation steps of the CPU restatement of the reference (oracle/, validated against the
+    unmodified reference by oracle/make_golden.py). Returns (steps timed, seconds per step, threads)."""
+    from oracle import dino_vit, splice_ref as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = make_cfg(model_name)
+    vit = dino_vit.build(model_name)
+    vsd = {k: v.detach() for k, v in vit.state_dict().items()}
+    from splice_b200.models.networks import define_G
+
+    torch.manual_seed(0)
+    net = define_G(cfg["init_type"], cfg["init_gain"])
+    params = {k: p.detach().clone().requires_grad_(True) for k, p in net.named_parameters()}
+    bufs = {k: v for k, v in net.state_dict().items() if k not in params}
+    m = {k: torch.zeros_like(p) for k, p in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    A, B = synth_image(1000, side, 8), synth_image(1001, side, 16)
+    sched = crop_schedule(A, B, 8, seed=0)
+    lam = R.active_lambdas(cfg, 1, None)
+
+    def one(step):
+        a, b = sched[step % len(sched)]
+        sd = {**bufs, **params}
+        outs = {"x_global": R.generator_forward(sd, a), "y_global": R.generator_forward(sd, b)}
+        s_idx = 2 + step + (1 if (2 + step) % cfg["entire_A_every"] == 0 else 0)   # steady-state steps only
+        loss = R.loss_g(vsd, cfg, R.active_lambdas(cfg, s_idx, lam), outs, {"A_global": a, "B_global": b})["loss"]
+        grads = torch.autograd.grad(loss, list(params.values()))
+        with torch.no_grad():
+            for (k, p), g in zip(params.items(), grads):
+                R.adam_step(p, g, m[k], v[k], step + 1, cfg["lr"], cfg["optimizer_beta1"], cfg["optimizer_beta2"])
+        return float(loss)
+
+    t_w = time.perf_counter()
+    for i in range(n_warm):
+        one(i)
+    est = (time.perf_counter() - t_w) / max(n_warm, 1)
+    n = n_steps if est <= 0 else max(1, min(n_steps, int(budget_s / max(est, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(n):
+        one(n_warm + i)
+    dt = (time.perf_counter() - t0) / n
+    return n, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank: int) -> None:
+    if rank != 0:
+        return
+    n, dt, threads = cpu_reference_steps("dino_vitb8", 224, n_warm=1, n_steps=args.steps, budget_s=150.0)
+    val = 1.0 / dt
+    sample = (f"{n} full optimisation steps (1 warm-up) of the CPU oracle port of the reference loop at configs[1] shapes "
+              f"(requested --steps {args.steps}; bounded to ~150 s)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic pair (SURVEY §8d), seeded random DINO-style ViT weights",
+            "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, steady-state steps", "steps_timed": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# splice_b200 arm
+# --------------------------------------------------------------------------------------------------
+def run_native(args, rank: int, local_rank: int, world: int) -> None:
+    import torch.distributed as dist
+
+    from splice_b200 import _lib
+    from splice_b200.dino_init import random_dino_state_dict
+    from splice_b200.engine import pack_vit_weights
+    from splice_b200.models.model import Model
+    from splice_b200.util.losses import LossG
+    from splice_b200.util.util import get_optimizer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model_name, side = "dino_vitb8", 224
+    cfg = make_cfg(model_name)
+
+    # ViT weights: rank 0 materialises them, one NCCL broadcast of the packed buffer
+    sd0 = random_dino_state_dict(model_name)
+    if rank == 0:
+        packed = pack_vit_weights(sd0, dev)
+    else:
+        packed = torch.empty(sum(v.numel() for v in sd0.values()), device=dev)
+    if world > 1:
+        dist.broadcast(packed, src=0)
+    torch.manual_seed(rank)
+    model = Model(cfg)
+    crit = LossG(cfg, packed=packed)
+    opt = get_optimizer(cfg, model.netG.parameters())
+
+    A, B = synth_image(1000 + 2 * rank, side, 8), synth_image(1001 + 2 * rank, side, 16)
+    sched_host = [(a.pin_memory(), b.pin_memory()) for a, b in crop_schedule(A, B, 32, seed=rank)]
+    sched_dev = [(a.to(dev), b.to(dev)) for a, b in sched_host]
+    A_host, A_dev = A[None].pin_memory(), A[None].to(dev)
+    every = cfg["entire_A_every"]
+
+    def step_resident(i: int):
+        a, b = sched_dev[i % len(sched_dev)]
+        inputs = {"step": torch.tensor([float(i)]), "A_global": a, "B_global": b}  # step stays on the host: no sync
+        if i % every == 0:
+            inputs["A"] = A_dev
+        opt.zero_grad()
+        losses = crit(model(inputs), inputs)
+        losses["loss"].backward()
+        opt.step()
+        return losses["loss"]
+
+    def step_e2e(i: int):
+        a, b = sched_host[i % len(sched_host)]
+        inputs = {"step": torch.tensor([float(i)]), "A_global": a, "B_global": b}
+        if i % every == 0:
+            inputs["A"] = A_host
+        nbytes = sum(v.numel() * v.element_size() for v in inputs.values())
+        inputs = {k: v.to(dev, non_blocking=True) for k, v in inputs.items()}   # train.py:54-55
+        opt.zero_grad()
+        losses = crit(model(inputs), inputs)
+        val = losses["loss"].item()                                                # train.py:67
+        losses["loss"].backward()
+        opt.step()
+        return nbytes, val
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, first: int, k: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        extra = 0
+        for i in range(first, first + k):
+            r = fn(i)
+            if isinstance(r, tuple):
+                extra += r[0]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = tm.item()
+        return ms, extra
+
+    # warm-up from step 0 (covers the cls-warmup step, an "entire" step and every crop shape), then the timed legs
+    i0 = 0
+    for i in range(args.warmup):
+        step_resident(i0 + i)
+    i0 += args.warmup
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.splice_launch_count_reset()
+    ms, _ = timed(step_resident, i0, args.steps)
+    launches = _lib.splice_launch_count()
+    clocks = sampler.stop() if rank == 0 else {}
+    i0 += args.steps
+    k_e2e = max(10, min(args.steps, 200))
+    for i in range(3):
+        step_e2e(i0 + i)
+    i0 += 3
+    ms_e2e, h2d = timed(step_e2e, i0, k_e2e)
+    i0 += k_e2e
+
+    # roofline leg: per-kernel-class CUDA-event timing inside the engine over a few live steps
+    eng = crit.engine
+    eng.profile_enable(True)
+    n_prof = 20
+    for i in range(n_prof):
+        step_resident(i0 + i)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    i0 += n_prof
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    g = prof["gemm_tcgen05"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    it_s = world * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic pair (SURVEY §8d), seeded random DINO-style ViT weights",
+        "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, reference step schedule (every 75th step adds the "
+                               "entire-image terms), crops 213-224 px", "pairs": world, "parallelism": f"{world} independent pair(s), 1/GPU",
+                   "l2": "per-step working set (~0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
+                   "generator": "torch autograd + cuDNN (interim, round 1)"},
+        "e2e": {"value": world * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": 4,
+                "steps": k_e2e, "note": "train.py loop body: pinned host crops -> device each step, loss.item() each step"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peaks["tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                     "launches_per_step": g["count"] / n_prof, "avg_launch_us": 1e3 * g["ms"] / max(g["count"], 1),
+                     "algorithmic_gflop_per_launch": g["flops"] / max(g["count"], 1) / 1e9,
+                     "loop_vit_tflops": VIT_GFLOP_PER_STEP * (it_s / world) / 1e3,
+                     "loop_frac_of_peak": VIT_GFLOP_PER_STEP * (it_s / world) / 1e3 / peaks["tflops"]},
+        "kernel_classes_ms_per_step": {k: v["ms"] / n_prof for k, v in prof.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n, dt, threads = cpu_reference_steps(model_name, side, n_warm=1, n_steps=3, budget_s=25.0)
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n} full optimisation steps (after 1 warm-up) of the CPU oracle port at the same shapes"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=80)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); the splice_b200 arm has no CPU fallback")
+    if args.warmup < 3:
+        raise SystemExit("--warmup must be >= 3")
+    run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

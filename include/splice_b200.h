@@ -134,6 +134,17 @@ typedef struct SpliceVitBackwardArgs {
 } SpliceVitBackwardArgs;
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* args, void* stream);
 
+/* Per-kernel-class CUDA-event timing inside the engine (bench.py's roofline leg; off by default).
+ * classes: 0 GEMM (tcgen05), 1 attention fwd, 2 attention bwd, 3 row-wise (LayerNorm), 4 preprocess */
+typedef struct SpliceProfileEntry {
+    long long count;   /* launches */
+    double ms;         /* summed device time */
+    double flops;      /* summed algorithmic FLOPs */
+    double bytes;      /* summed algorithmic bytes */
+} SpliceProfileEntry;
+SPLICE_API int splice_vit_profile_enable(void* ctx, int on);
+SPLICE_API int splice_vit_profile_read(void* ctx, SpliceProfileEntry* out, int n);
+
 /* ---- losses ----------------------------------------------------------------------------------------- */
 /* loss[0] = mean((S(keys_x) - S(keys_a))^2), S = cosine self-similarity of the rows of a [t,D] key matrix;
  * dkeys_x = coef * dloss/dkeys_x (fp32 [t,D]) or NULL.  ref: attn_cosine_sim models/extractor.py:4-9,

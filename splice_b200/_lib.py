@@ -84,6 +84,10 @@ class SpliceVitBackwardArgs(C.Structure):
     ]
 
 
+class SpliceProfileEntry(C.Structure):
+    _fields_ = [("count", c_longlong), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -117,6 +121,8 @@ splice_vit_create = _sig("splice_vit_create", c_int,
 splice_vit_destroy = _sig("splice_vit_destroy", c_int, [c_void_p])
 splice_vit_forward = _sig("splice_vit_forward", c_int, [c_void_p, C.POINTER(SpliceVitForwardArgs), c_void_p])
 splice_vit_backward = _sig("splice_vit_backward", c_int, [c_void_p, C.POINTER(SpliceVitBackwardArgs), c_void_p])
+splice_vit_profile_enable = _sig("splice_vit_profile_enable", c_int, [c_void_p, c_int])
+splice_vit_profile_read = _sig("splice_vit_profile_read", c_int, [c_void_p, C.POINTER(SpliceProfileEntry), c_int])
 splice_loss_ssim = _sig("splice_loss_ssim", c_int,
                         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p])
 splice_loss_mse = _sig("splice_loss_mse", c_int,
@@ -136,7 +142,7 @@ EXPORTS = [
     "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd", "splice_resize_normalize",
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
-    "splice_adam_step",
+    "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
 
 

@@ -140,6 +140,23 @@ SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, vo
     return e->backward(v, (cudaStream_t)stream);
 }
 
+SPLICE_API int splice_vit_profile_enable(void* ctx, int on) {
+    SPLICE_REQUIRE(ctx, "splice_vit_profile_enable: null ctx");
+    static_cast<VitEngine*>(ctx)->profile_enable(on != 0);
+    return SPLICE_OK;
+}
+SPLICE_API int splice_vit_profile_read(void* ctx, SpliceProfileEntry* out, int n) {
+    SPLICE_REQUIRE(ctx && out && n > 0, "splice_vit_profile_read: bad argument");
+    ProfTotals t[PROF_NCAT];
+    int rc = static_cast<VitEngine*>(ctx)->profile_read(t, PROF_NCAT);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        if (i < PROF_NCAT) { out[i].count = t[i].count; out[i].ms = t[i].ms; out[i].flops = t[i].flops; out[i].bytes = t[i].bytes; }
+        else { out[i].count = 0; out[i].ms = 0; out[i].flops = 0; out[i].bytes = 0; }
+    }
+    return SPLICE_OK;
+}
+
 // ---- losses --------------------------------------------------------------------------------------
 namespace {
 struct SsimWs {

@@ -204,6 +204,50 @@ int VitEngine::configure(Slot& s, int S, int t, int n_grad) {
     return SPLICE_OK;
 }
 
+void VitEngine::profile_enable(bool on) { prof_on_ = on; }
+void VitEngine::prof_begin(int cat, double flops, double bytes, cudaStream_t st) {
+    if (!prof_on_) return;
+    ProfRec r;
+    r.cat = cat; r.flops = flops; r.bytes = bytes;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!prof_pool_.empty()) { e = prof_pool_.back(); prof_pool_.pop_back(); } else cudaEventCreate(&e);
+        return e;
+    };
+    r.e0 = get(); r.e1 = get();
+    cudaEventRecord(r.e0, st);
+    prof_pending_.push_back(r);
+}
+void VitEngine::prof_end(cudaStream_t st) {
+    if (!prof_on_ || prof_pending_.empty()) return;
+    cudaEventRecord(prof_pending_.back().e1, st);
+}
+int VitEngine::profile_read(ProfTotals* out, int n) {
+    SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
+    for (auto& r : prof_pending_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            ProfTotals& t = prof_tot_[r.cat];
+            t.count += 1; t.ms += ms; t.flops += r.flops; t.bytes += r.bytes;
+        }
+        prof_pool_.push_back(r.e0); prof_pool_.push_back(r.e1);
+    }
+    prof_pending_.clear();
+    for (int i = 0; i < n && i < PROF_NCAT; ++i) out[i] = prof_tot_[i];
+    for (int i = 0; i < PROF_NCAT; ++i) prof_tot_[i] = ProfTotals{0, 0.0, 0.0, 0.0};
+    return SPLICE_OK;
+}
+
+// profiled launch wrappers
+#define PROF(cat, flops, bytes, expr)                   \
+    do {                                                \
+        prof_begin((cat), (flops), (bytes), stream);    \
+        int _rc = (expr);                               \
+        prof_end(stream);                               \
+        if (_rc) return _rc;                            \
+    } while (0)
+#define GEMM_FLOPS(M, N, K) (2.0 * (double)(M) * (double)(N) * (double)(K))
+
 #define RC(expr)                 \
     do {                         \
         int _rc = (expr);        \
@@ -234,34 +278,34 @@ int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
         GemmEpilogue ep;
         ep.c32 = s.x0[0]; ep.ldc32 = D; ep.bias = pe_b_;
         ep.rows_per_seq = t - 1; ep.pos = pos; ep.ldpos = D;
-        RC(gemm_bf16_tn(s.patches, pp3, pe_w_, pp3, S * (t - 1), D, pp3, ep, a.gemm_impl, 0, stream));
+        PROF(PROF_GEMM, GEMM_FLOPS(S * (t - 1), D, pp3), 0.0, gemm_bf16_tn(s.patches, pp3, pe_w_, pp3, S * (t - 1), D, pp3, ep, a.gemm_impl, 0, stream));
     }
     for (int l = 0; l < depth; ++l) {
         const LayerW& L = L_[l];
-        RC(layernorm_fwd(s.x0[l], L.ln1_g, L.ln1_b, s.a16, s.st1[l], M, D, d_.ln_eps, stream));
+        PROF(PROF_ROWWISE, 0.0, 6.0 * M * D, layernorm_fwd(s.x0[l], L.ln1_g, L.ln1_b, s.a16, s.st1[l], M, D, d_.ln_eps, stream));
         {
             GemmEpilogue ep;
             ep.c16 = s.qkv[l]; ep.ldc16 = 3 * D; ep.bias = L.qkv_b;
             if (a.qkv32_all) { ep.c32 = a.qkv32_all + (size_t)l * M * 3 * D; ep.ldc32 = 3 * D; }
             if (l == depth - 1 && a.keys32) { ep.slice32 = a.keys32; ep.slice_c0 = D; ep.slice_c1 = 2 * D; ep.ldslice = D; }
-            RC(gemm_bf16_tn(s.a16, D, L.qkv_w, D, M, 3 * D, D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(M, 3 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.qkv_w, D, M, 3 * D, D, ep, a.gemm_impl, 0, stream));
         }
-        RC(attention_fwd(s.qkv[l], s.o[l], s.lse[l], S, t, D, H, stream));
+        PROF(PROF_ATTN_FWD, 4.0 * S * (double)t * t * D, 0.0, attention_fwd(s.qkv[l], s.o[l], s.lse[l], S, t, D, H, stream));
         {
             GemmEpilogue ep;
             ep.c32 = s.x1[l]; ep.ldc32 = D; ep.bias = L.proj_b; ep.residual = s.x0[l]; ep.ldr = D;
-            RC(gemm_bf16_tn(s.o[l], D, L.proj_w, D, M, D, D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(M, D, D), 0.0, gemm_bf16_tn(s.o[l], D, L.proj_w, D, M, D, D, ep, a.gemm_impl, 0, stream));
         }
-        RC(layernorm_fwd(s.x1[l], L.ln2_g, L.ln2_b, s.a16, s.st2[l], M, D, d_.ln_eps, stream));
+        PROF(PROF_ROWWISE, 0.0, 6.0 * M * D, layernorm_fwd(s.x1[l], L.ln2_g, L.ln2_b, s.a16, s.st2[l], M, D, d_.ln_eps, stream));
         {
             GemmEpilogue ep;
             ep.c16 = s.h16; ep.ldc16 = 4 * D; ep.bias = L.fc1_b; ep.act = GEMM_ACT_GELU; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
-            RC(gemm_bf16_tn(s.a16, D, L.fc1_w, D, M, 4 * D, D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(M, 4 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.fc1_w, D, M, 4 * D, D, ep, a.gemm_impl, 0, stream));
         }
         {
             GemmEpilogue ep;
             ep.c32 = s.x0[l + 1]; ep.ldc32 = D; ep.bias = L.fc2_b; ep.residual = s.x1[l]; ep.ldr = D;
-            RC(gemm_bf16_tn(s.h16, 4 * D, L.fc2_w, 4 * D, M, D, 4 * D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(M, D, 4 * D), 0.0, gemm_bf16_tn(s.h16, 4 * D, L.fc2_w, 4 * D, M, D, 4 * D, ep, a.gemm_impl, 0, stream));
         }
         if (a.block32_all)
             SPLICE_CHECK_CUDA(cudaMemcpyAsync(a.block32_all + (size_t)l * M * D, s.x0[l + 1], (size_t)M * D * sizeof(float),
@@ -296,20 +340,21 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
             {   // d(gelu out) = g W2 ; d(pre) = . * gelu'(pre)
                 GemmEpilogue ep;
                 ep.c16 = s.dh16; ep.ldc16 = 4 * D; ep.act = GEMM_ACT_GELU_GRAD; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
-                RC(gemm_bf16_tn(s.g16, D, L.fc2_wT, D, Mg, 4 * D, D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mg, 4 * D, D), 0.0, gemm_bf16_tn(s.g16, D, L.fc2_wT, D, Mg, 4 * D, D, ep, a.gemm_impl, 0, stream));
             }
             {   // d(LN2 out) = d(pre) W1
                 GemmEpilogue ep;
                 ep.c32 = s.da; ep.ldc32 = D;
-                RC(gemm_bf16_tn(s.dh16, 4 * D, L.fc1_wT, 4 * D, Mg, D, 4 * D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, 4 * D), 0.0, gemm_bf16_tn(s.dh16, 4 * D, L.fc1_wT, 4 * D, Mg, D, 4 * D, ep, a.gemm_impl, 0, stream));
             }
-            RC(layernorm_bwd(s.da, s.x1[l], s.st2[l], L.ln2_g, s.g, s.g, s.g16, Mg, D, stream));
+            PROF(PROF_ROWWISE, 0.0, 18.0 * Mg * D, layernorm_bwd(s.da, s.x1[l], s.st2[l], L.ln2_g, s.g, s.g, s.g16, Mg, D, stream));
             {   // d(attn out) = g Wproj
                 GemmEpilogue ep;
                 ep.c16 = s.do16; ep.ldc16 = D;
-                RC(gemm_bf16_tn(s.g16, D, L.proj_wT, D, Mg, D, D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, D), 0.0, gemm_bf16_tn(s.g16, D, L.proj_wT, D, Mg, D, D, ep, a.gemm_impl, 0, stream));
             }
-            RC(attention_bwd(s.qkv[l], s.o[l], s.do16, s.lse[l], s.delta, s.dqkv16, Sg, t, D, H, stream));
+            PROF(PROF_ATTN_BWD, 8.0 * Sg * (double)t * t * D, 0.0,
+                 attention_bwd(s.qkv[l], s.o[l], s.do16, s.lse[l], s.delta, s.dqkv16, Sg, t, D, H, stream));
         } else {
             // nothing flows back from the block output (keys-only objective): d(qkv) starts at zero
             SPLICE_CHECK_CUDA(cudaMemsetAsync(s.dqkv16, 0, (size_t)Mg * 3 * D * sizeof(bf16), stream));
@@ -319,15 +364,15 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
         {   // d(LN1 out) = d(qkv) Wqkv
             GemmEpilogue ep;
             ep.c32 = s.da; ep.ldc32 = D;
-            RC(gemm_bf16_tn(s.dqkv16, 3 * D, L.qkv_wT, 3 * D, Mg, D, 3 * D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, 3 * D), 0.0, gemm_bf16_tn(s.dqkv16, 3 * D, L.qkv_wT, 3 * D, Mg, D, 3 * D, ep, a.gemm_impl, 0, stream));
         }
-        RC(layernorm_bwd(s.da, s.x0[l], s.st1[l], L.ln1_g, s.g, s.g, s.g16, Mg, D, stream));
+        PROF(PROF_ROWWISE, 0.0, 18.0 * Mg * D, layernorm_bwd(s.da, s.x0[l], s.st1[l], L.ln1_g, s.g, s.g, s.g16, Mg, D, stream));
         have_g = true;
     }
     {   // d(patch pixels) = g Wpe  (cls rows produce rows that the adjoint resampler never reads)
         GemmEpilogue ep;
         ep.c32 = s.dpatch; ep.ldc32 = pp3;
-        RC(gemm_bf16_tn(s.g16, D, pe_wT_, D, Mg, pp3, D, ep, a.gemm_impl, 0, stream));
+        PROF(PROF_GEMM, GEMM_FLOPS(Mg, pp3, D), 0.0, gemm_bf16_tn(s.g16, D, pe_wT_, D, Mg, pp3, D, ep, a.gemm_impl, 0, stream));
     }
     for (int i = 0; i < Sg; ++i) {
         SPLICE_REQUIRE(a.grads[i].h == s.imgs[i].h && a.grads[i].w == s.imgs[i].w,

@@ -37,8 +37,16 @@ struct VitBackwardArgs {
     int gemm_impl = 0;
 };
 
+enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN_FWD = 1, PROF_ATTN_BWD = 2, PROF_ROWWISE = 3, PROF_PREPROC = 4, PROF_NCAT = 5 };
+struct ProfTotals { long long count; double ms; double flops; double bytes; };
+
 class VitEngine {
 public:
+    // per-kernel-class CUDA-event timing (off by default; bench.py turns it on for a separate measurement leg)
+    void profile_enable(bool on);
+    int profile_read(ProfTotals* out, int n);   // synchronises, accumulates and clears the pending events
+    void prof_begin(int cat, double flops, double bytes, cudaStream_t st);
+    void prof_end(cudaStream_t st);
     static int create(VitEngine** out, const VitDesc& d, const float* packed_dev, size_t n_floats, cudaStream_t stream);
     ~VitEngine();
     static size_t packed_size(const VitDesc& d);
@@ -81,6 +89,11 @@ private:
     Slot slots_[4];
     void* loss_ws_ = nullptr;
     size_t loss_ws_bytes_ = 0;
+    struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };
+    bool prof_on_ = false;
+    std::vector<ProfRec> prof_pending_;
+    std::vector<cudaEvent_t> prof_pool_;
+    ProfTotals prof_tot_[PROF_NCAT] = {};
 };
 
 }  // namespace splice

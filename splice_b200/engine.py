@@ -63,8 +63,10 @@ def interpolate_pos_embed(pos_embed: torch.Tensor, patch: int, h: int, w: int) -
 class VitEngine:
     """Owns one `splice_vit_*` context on the current CUDA device."""
 
-    def __init__(self, model_name: str, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda",
-                 packed: Optional[torch.Tensor] = None, gemm_impl: int = 0):
+    def __init__(self, model_name: str, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 device: torch.device | str = "cuda", packed: Optional[torch.Tensor] = None, gemm_impl: int = 0):
+        """Either `state_dict` (the 150 DINO tensors) or `packed` (the flat fp32 buffer of pack_vit_weights, e.g.
+        as received from the rank-0 NCCL broadcast) must be given."""
         if model_name not in DINO_ARCH:
             raise NotImplementedError(f"unsupported DINO model {model_name!r}")
         if not torch.cuda.is_available():
@@ -73,9 +75,13 @@ class VitEngine:
         self.patch, self.dim, self.heads = DINO_ARCH[model_name]
         self.device = torch.device(device)
         self.gemm_impl = gemm_impl
-        self.pos_embed = state_dict["pos_embed"].detach().to(self.device, torch.float32)
-        self.n_pos = self.pos_embed.shape[1]
-        self.packed = packed if packed is not None else pack_vit_weights(state_dict, self.device)
+        if packed is None:
+            if state_dict is None:
+                raise ValueError("VitEngine needs a state_dict or a packed weight buffer")
+            packed = pack_vit_weights(state_dict, self.device)
+        self.packed = packed.to(self.device, torch.float32).contiguous()
+        self.n_pos = 1 + (224 // self.patch) ** 2          # DINO checkpoints are trained at 224 px
+        self.pos_embed = self.packed[self.dim:self.dim + self.n_pos * self.dim].view(1, self.n_pos, self.dim)
         self.desc = _lib.SpliceVitDesc(self.patch, self.dim, self.heads, DEPTH, self.n_pos, LN_EPS)
         expect = _lib.splice_vit_packed_floats(C.byref(self.desc))
         if self.packed.numel() != expect:
@@ -177,6 +183,19 @@ class VitEngine:
         a.dkeys32, a.dcls32, a.grads, a.gemm_impl = ptr(dkeys), ptr(dcls), arr, self.gemm_impl
         check(_lib.splice_vit_backward(self._ctx, C.byref(a), cur_stream()), "splice_vit_backward")
         return grads
+
+    # ---- profiling -------------------------------------------------------------------------------------
+    PROFILE_CLASSES = ("gemm_tcgen05", "attention_fwd", "attention_bwd", "rowwise_layernorm", "preprocess")
+
+    def profile_enable(self, on: bool) -> None:
+        check(_lib.splice_vit_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self) -> Dict[str, dict]:
+        n = len(self.PROFILE_CLASSES)
+        arr = (_lib.SpliceProfileEntry * n)()
+        check(_lib.splice_vit_profile_read(self._ctx, arr, n))
+        return {name: {"count": arr[i].count, "ms": arr[i].ms, "flops": arr[i].flops, "bytes": arr[i].bytes}
+                for i, name in enumerate(self.PROFILE_CLASSES)}
 
     # ---- losses ------------------------------------------------------------------------------------
     def loss_ssim(self, keys_x: torch.Tensor, keys_a: torch.Tensor, coef: float, loss_out: torch.Tensor,

@@ -35,9 +35,11 @@ class VitExtractor:
 
     _engines: List[VitEngine] = []
 
-    def __init__(self, model_name, device, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+    def __init__(self, model_name, device, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 packed: Optional[torch.Tensor] = None):
         """ref extractor.py:19-29. `state_dict` (optional, extension): DINO weights to use instead of
-        `torch.hub.load('facebookresearch/dino:main', model_name)`; with SPLICE_B200_RANDOM_DINO=1 a seeded
+        `torch.hub.load('facebookresearch/dino:main', model_name)`; `packed`: the same weights as one flat
+        fp32 buffer (engine.pack_vit_weights; what rank 0 broadcasts over NCCL); with SPLICE_B200_RANDOM_DINO=1 a seeded
         random DINO-style init is used when the hub is unreachable (benchmarks / offline tests)."""
         if model_name not in DINO_ARCH:
             raise NotImplementedError(f"model {model_name!r} is not a DINO ViT supported by splice_b200")
@@ -46,7 +48,7 @@ class VitExtractor:
         if self.device.type != "cuda":
             raise RuntimeError("splice_b200.VitExtractor runs on sm_100a only; there is no CPU fallback")
         self.model = None
-        if state_dict is None:
+        if state_dict is None and packed is None:
             if os.environ.get("SPLICE_B200_RANDOM_DINO", "0") == "1":
                 from ..dino_init import random_dino_state_dict
 
@@ -55,7 +57,7 @@ class VitExtractor:
                 self.model = torch.hub.load('facebookresearch/dino:main', model_name).to(device)
                 self.model.eval()
                 state_dict = self.model.state_dict()
-        self.engine = VitEngine(model_name, state_dict, self.device)
+        self.engine = VitEngine(model_name, state_dict, self.device, packed=packed)
         VitExtractor._engines.append(self.engine)
         self.hook_handlers = []
         self.layers_dict = {key: list(range(12)) for key in VitExtractor.KEY_LIST}

@@ -75,10 +75,11 @@ class _Objective(torch.autograd.Function):
 
 class LossG(torch.nn.Module):
 
-    def __init__(self, cfg, state_dict=None):
+    def __init__(self, cfg, state_dict=None, packed=None):
         super().__init__()
         self.cfg = cfg
-        self.extractor = VitExtractor(model_name=cfg['dino_model_name'], device=device, state_dict=state_dict)
+        self.extractor = VitExtractor(model_name=cfg['dino_model_name'], device=device, state_dict=state_dict,
+                                      packed=packed)
         self.engine: VitEngine = self.extractor.engine
         self.global_transform = GlobalTransform(self.engine, cfg['dino_global_patch_size'])
         self.lambdas = dict(
