@@ -160,6 +160,28 @@ SPLICE_API int splice_keys_self_sim(void* ctx, const void* keys, int t, void* ou
 /* total[0] = sum_i weights_host[i] * terms[i], n <= 8.  ref: LossG.forward util/losses.py:46-72 */
 SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream);
 
+/* ---- generator ------------------------------------------------------------------------------------- */
+/* The default-argument skip() U-Net (ref: models/unet/skip.py:4-102, models/unet/common.py:11-124, called from
+ * Model.forward models/model.py:12-25). Parameters are borrowed per call in netG.parameters() order (112 fp32
+ * tensors), BatchNorm buffers in module order (30 layers). BatchNorm always uses batch statistics (the reference
+ * never calls .eval()); running statistics are updated like nn.BatchNorm2d(momentum=0.1) when update_running != 0. */
+#define SPLICE_GEN_PARAMS 112
+#define SPLICE_GEN_BN 30
+typedef struct SpliceGenPointers {
+    void* param[SPLICE_GEN_PARAMS];
+    void* grad[SPLICE_GEN_PARAMS];            /* fp32, ACCUMULATED into by splice_gen_backward; may be NULL for forward */
+    void* running_mean[SPLICE_GEN_BN];
+    void* running_var[SPLICE_GEN_BN];
+    void* num_batches_tracked[SPLICE_GEN_BN]; /* int64 scalars */
+} SpliceGenPointers;
+SPLICE_API int splice_gen_create(void** ctx);
+SPLICE_API int splice_gen_destroy(void* ctx);
+/* out[N,3,H,W] = netG(x[N,3,H,W]); keep != 0 retains the activations in `slot` (0..3) for splice_gen_backward */
+SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const void* x, int N, int H, int W, void* out,
+                                  int slot, int keep, int update_running, void* stream);
+/* parameter gradients += d loss / d params given dout[N,3,H,W] = d loss / d out of the forward kept in `slot` */
+SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream);
+
 /* ---- optimiser -------------------------------------------------------------------------------------- */
 /* One Adam step over n_tensors fp32 tensors (host arrays of device pointers / element counts).
  * `step` is the 1-based step count AFTER the increment.  ref: get_optimizer util/util.py:28-32 -> torch.optim.Adam */

@@ -88,6 +88,15 @@ class SpliceProfileEntry(C.Structure):
     _fields_ = [("count", c_longlong), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
+GEN_PARAMS, GEN_BN = 112, 30
+
+
+class SpliceGenPointers(C.Structure):
+    _fields_ = [("param", c_void_p * GEN_PARAMS), ("grad", c_void_p * GEN_PARAMS),
+                ("running_mean", c_void_p * GEN_BN), ("running_var", c_void_p * GEN_BN),
+                ("num_batches_tracked", c_void_p * GEN_BN)]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -130,6 +139,12 @@ splice_loss_mse = _sig("splice_loss_mse", c_int,
 splice_keys_self_sim = _sig("splice_keys_self_sim", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p])
 splice_weighted_total = _sig("splice_weighted_total", c_int, [c_void_p, C.POINTER(c_float), c_int, c_void_p, c_void_p])
 
+splice_gen_create = _sig("splice_gen_create", c_int, [C.POINTER(c_void_p)])
+splice_gen_destroy = _sig("splice_gen_destroy", c_int, [c_void_p])
+splice_gen_forward = _sig("splice_gen_forward", c_int,
+                          [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                           c_void_p])
+splice_gen_backward = _sig("splice_gen_backward", c_int, [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_void_p])
 splice_adam_step = _sig("splice_adam_step", c_int,
                         [C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
                          C.POINTER(c_int), c_int, c_int, c_float, c_float, c_float, c_float, c_void_p])
@@ -142,6 +157,7 @@ EXPORTS = [
     "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd", "splice_resize_normalize",
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
+    "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
 

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "elementwise.h"
 #include "gemm.h"
+#include "generator.h"
 #include "losses.h"
 #include "preprocess.h"
 #include "splice_b200.h"
@@ -246,6 +247,44 @@ SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows
 
 SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream) {
     return weighted_total((const float*)terms, weights_host, n, (float*)total, (cudaStream_t)stream);
+}
+
+// ---- generator -----------------------------------------------------------------------------------
+static void to_gen_ptrs(const SpliceGenPointers* p, GenPointers* g) {
+    for (int i = 0; i < GEN_PARAMS; ++i) { g->param[i] = (float*)p->param[i]; g->grad[i] = (float*)p->grad[i]; }
+    for (int i = 0; i < GEN_BN; ++i) {
+        g->running_mean[i] = (float*)p->running_mean[i]; g->running_var[i] = (float*)p->running_var[i];
+        g->num_batches_tracked[i] = (long long*)p->num_batches_tracked[i];
+    }
+}
+SPLICE_API int splice_gen_create(void** ctx) {
+    SPLICE_REQUIRE(ctx, "splice_gen_create: null ctx");
+    static_assert(SPLICE_GEN_PARAMS == GEN_PARAMS && SPLICE_GEN_BN == GEN_BN, "header / engine mismatch");
+    *ctx = new GenEngine();
+    return SPLICE_OK;
+}
+SPLICE_API int splice_gen_destroy(void* ctx) {
+    delete static_cast<GenEngine*>(ctx);
+    return SPLICE_OK;
+}
+SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const void* x, int N, int H, int W, void* out, int slot,
+                                  int keep, int update_running, void* stream) {
+    SPLICE_REQUIRE(ctx && p, "splice_gen_forward: null argument");
+    GenPointers g;
+    to_gen_ptrs(p, &g);
+    for (int i = 0; i < GEN_PARAMS; ++i) SPLICE_REQUIRE(g.param[i], "splice_gen_forward: parameter %d is null", i);
+    if (update_running)
+        for (int i = 0; i < GEN_BN; ++i)
+            SPLICE_REQUIRE(g.running_mean[i] && g.running_var[i] && g.num_batches_tracked[i], "splice_gen_forward: BN buffer %d is null", i);
+    return static_cast<GenEngine*>(ctx)->forward(g, (const float*)x, N, H, W, (float*)out, slot, keep != 0, update_running != 0,
+                                                 (cudaStream_t)stream);
+}
+SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream) {
+    SPLICE_REQUIRE(ctx && p, "splice_gen_backward: null argument");
+    GenPointers g;
+    to_gen_ptrs(p, &g);
+    for (int i = 0; i < GEN_PARAMS; ++i) SPLICE_REQUIRE(g.param[i] && g.grad[i], "splice_gen_backward: parameter/grad %d is null", i);
+    return static_cast<GenEngine*>(ctx)->backward(g, (const float*)dout, slot, (cudaStream_t)stream);
 }
 
 // ---- optimiser -----------------------------------------------------------------------------------

@@ -1,0 +1,67 @@
+// splice_b200 — native conv generator (the reference's default-argument skip() U-Net), see generator.cu
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace splice {
+
+static constexpr int GEN_SCALES = 5;
+static constexpr int GEN_PARAMS = 112;     // netG.parameters() order (oracle/splice_ref.py generator_param_keys)
+static constexpr int GEN_BN = 30;          // BatchNorm2d layers, module order
+static constexpr int GEN_SLOTS = 4;
+
+struct GenPointers {
+    float* param[GEN_PARAMS];
+    float* grad[GEN_PARAMS];               // accumulated into (+=); may be null when only forward is used
+    float* running_mean[GEN_BN];
+    float* running_var[GEN_BN];
+    long long* num_batches_tracked[GEN_BN];
+};
+
+class GenEngine {
+public:
+    GenEngine();
+    ~GenEngine();
+    // x [N,3,H,W] -> out [N,3,H,W] (sigmoid). keep = activations stay in `slot` for backward().
+    int forward(const GenPointers& p, const float* x, int N, int H, int W, float* out, int slot, bool keep,
+                bool update_running, cudaStream_t stream);
+    // dout [N,3,H,W] -> parameter gradients accumulated into p.grad; dx (optional) = d loss / d input
+    int backward(const GenPointers& p, const float* dout, int slot, cudaStream_t stream);
+
+private:
+    struct Conv { int cin, cout, k, stride, pw, pb; };         // pw/pb: parameter indices of weight / bias
+    struct Bn { int c, pg, pb, idx; };                         // pg/pb: parameter indices of gamma / beta; idx: BN order
+    struct Scale {
+        Conv s, d1, d2, c1, c2;
+        Bn bs, bd1, bd2, bcat, bc1, bc2;
+        int cdeep;
+    };
+    struct ScaleBuf {
+        int h, w, hd, wd;                                      // this scale's input size and the down-sampled size
+        float *s_raw, *d1_raw, *d2_raw, *cat, *c1_raw, *c2_raw;
+        float *dA_s, *dA_d1, *dA_d2, *dcat, *dA_c1, *dA_c2;
+        float4 *k_s, *k_d1, *k_d2, *k_cat, *k_c1, *k_c2;       // per-channel (mean, invstd, a, b)
+        float2 *m_s, *m_d1, *m_d2, *m_cat, *m_c1, *m_c2;       // per-channel (m1, m2) of the BN backward
+    };
+    struct Slot {
+        int N = 0, H = 0, W = 0;
+        bool valid = false;
+        void* pool = nullptr;
+        size_t pool_bytes = 0;
+        const float* x = nullptr;
+        float* x_copy = nullptr;
+        float* out = nullptr;
+        ScaleBuf sb[GEN_SCALES];
+    };
+    int configure(Slot& s, int N, int H, int W);
+    int ensure_scratch(size_t bytes);
+
+    Scale sc_[GEN_SCALES];
+    Conv final_;
+    Slot slots_[GEN_SLOTS];
+    void* scratch_ = nullptr;      // partial-reduction scratch shared by all calls (stream-ordered reuse)
+    size_t scratch_bytes_ = 0;
+};
+
+}  // namespace splice

@@ -1,0 +1,170 @@
+"""Host-side glue between the generator's nn.Module tree (parameters, BatchNorm buffers, state_dict) and the
+native sm_100a generator engine (include/splice_b200.h: splice_gen_*).
+
+The module tree built by models/unet/skip.py only OWNS the tensors; `NativeSkip.forward` sends them by pointer
+to the engine. Parameter gradients are accumulated by the engine straight into the `.grad` buffers (views of
+one flat buffer), across the 2-3 generator calls of a step, like autograd's accumulation does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, cur_stream
+
+_KEEP_SLOTS = 3      # x_global, y_global, x_entire may be alive at once; slot 3 serves no-grad calls
+
+
+class _GenFn(torch.autograd.Function):
+    """netG(x) on the native engine. `anchor` (a parameter) only makes autograd schedule backward(); the
+    parameter gradients are written by the engine as a side effect, the way fused optimisers consume them."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, anchor: torch.Tensor, module: "NativeSkip"):
+        keep = torch.is_grad_enabled() and anchor.requires_grad
+        out, slot, token = module._run_forward(x, keep)
+        ctx.module, ctx.slot, ctx.token = module, slot, token
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: torch.Tensor):
+        ctx.module._run_backward(gout, ctx.slot, ctx.token)
+        return None, None, None
+
+
+class NativeSkip(nn.Sequential):
+    """nn.Sequential tree of the default-argument skip() whose forward runs on the native generator engine."""
+
+    def __init__(self):
+        super().__init__()
+        self._eng = None
+        self._ptrs = None
+        self._ptr_sig = None
+        self._flat_grad: Optional[torch.Tensor] = None
+        self._grad_views: List[torch.Tensor] = []
+        self._slot_tokens = [None] * 4
+        self._next_slot = 0
+        self._token = 0
+
+    # ---- pointer tables ----------------------------------------------------------------------------
+    def _param_list(self) -> List[torch.nn.Parameter]:
+        ps = list(self.parameters())
+        if len(ps) != _lib.GEN_PARAMS:
+            raise RuntimeError(f"NativeSkip expects {_lib.GEN_PARAMS} parameter tensors, found {len(ps)}")
+        return ps
+
+    def _bn_list(self) -> List[nn.BatchNorm2d]:
+        bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+        if len(bns) != _lib.GEN_BN:
+            raise RuntimeError(f"NativeSkip expects {_lib.GEN_BN} BatchNorm2d layers, found {len(bns)}")
+        return bns
+
+    def _engine(self):
+        if self._eng is None:
+            h = C.c_void_p()
+            check(_lib.splice_gen_create(C.byref(h)), "splice_gen_create")
+            self._eng = h
+        return self._eng
+
+    def _refresh_ptrs(self, need_grads: bool):
+        ps = self._param_list()
+        sig = (ps[0].data_ptr(), ps[55].data_ptr(), ps[-1].data_ptr(), ps[0].device,
+               None if not need_grads else (ps[0].grad.data_ptr() if ps[0].grad is not None else 0,
+                                            ps[-1].grad.data_ptr() if ps[-1].grad is not None else 0))
+        if self._ptrs is not None and sig == self._ptr_sig:
+            return self._ptrs
+        for p in ps:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("the native generator needs contiguous fp32 CUDA parameters (no CPU fallback): "
+                                   "move the model to a CUDA device")
+        t = _lib.SpliceGenPointers()
+        for i, p in enumerate(ps):
+            t.param[i] = p.data_ptr()
+            t.grad[i] = p.grad.data_ptr() if (need_grads and p.grad is not None) else None
+        for i, bn in enumerate(self._bn_list()):
+            t.running_mean[i] = bn.running_mean.data_ptr()
+            t.running_var[i] = bn.running_var.data_ptr()
+            t.num_batches_tracked[i] = bn.num_batches_tracked.data_ptr()
+        self._ptrs, self._ptr_sig = t, sig
+        return t
+
+    def _attach_grads(self):
+        """Make every p.grad a view into one flat buffer (allocated once); zero what was missing."""
+        ps = self._param_list()
+        if self._flat_grad is None or self._flat_grad.device != ps[0].device:
+            n = sum(p.numel() for p in ps)
+            self._flat_grad = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
+            self._grad_views, off = [], 0
+            for p in ps:
+                self._grad_views.append(self._flat_grad[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            for p, v in zip(ps, self._grad_views):
+                p._splice_flat_grad, p._splice_grad_view = self._flat_grad, v
+        missing = [i for i, p in enumerate(ps) if p.grad is None]
+        if len(missing) == len(ps):
+            self._flat_grad.zero_()
+            for p, v in zip(ps, self._grad_views):
+                p.grad = v
+            self._ptr_sig = None
+        elif missing:
+            for i in missing:
+                self._grad_views[i].zero_()
+                ps[i].grad = self._grad_views[i]
+            self._ptr_sig = None
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def _run_forward(self, x: torch.Tensor, keep: bool):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("netG expects [N,3,H,W]")
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        if not x.is_cuda:
+            raise RuntimeError("the native generator runs on sm_100a only; there is no CPU fallback")
+        n, _, h, w = x.shape
+        out = torch.empty_like(x)
+        if keep:
+            slot = self._next_slot
+            self._next_slot = (self._next_slot + 1) % _KEEP_SLOTS
+        else:
+            slot = 3
+        self._token += 1
+        self._slot_tokens[slot] = self._token
+        t = self._refresh_ptrs(need_grads=False)
+        check(_lib.splice_gen_forward(self._engine(), C.byref(t), x.data_ptr(), n, h, w, out.data_ptr(), slot,
+                                      1 if keep else 0, 1 if self.training else 0, cur_stream()), "splice_gen_forward")
+        return out, slot, self._token
+
+    def _run_backward(self, gout: torch.Tensor, slot: int, token: int):
+        if self._slot_tokens[slot] != token:
+            raise RuntimeError("generator activations were overwritten: more than 3 netG calls were kept alive "
+                               "before their backward pass")
+        gout = gout.detach()
+        if gout.dtype != torch.float32 or not gout.is_contiguous():
+            gout = gout.float().contiguous()
+        self._attach_grads()
+        t = self._refresh_ptrs(need_grads=True)
+        check(_lib.splice_gen_backward(self._engine(), C.byref(t), gout.data_ptr(), slot, cur_stream()),
+              "splice_gen_backward")
+        self._slot_tokens[slot] = None
+
+    def forward(self, input):
+        anchor = next(self.parameters())
+        return _GenFn.apply(input, anchor, self)
+
+    def forward_reference_ops(self, input):
+        """The same tree evaluated module by module with torch ops (tests only: isolates engine bugs)."""
+        return nn.Sequential.forward(self, input)
+
+    def __del__(self):
+        eng = getattr(self, "_eng", None)
+        if eng:
+            try:
+                torch.cuda.synchronize()
+                _lib.splice_gen_destroy(eng)
+            except Exception:  # noqa: BLE001
+                pass

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import torch.nn as nn
 
+from ...generator import NativeSkip
 from .common import Concat, act, bn, conv
 
 
@@ -64,7 +65,14 @@ def skip(
         if not last:
             fill_level(nxt, i + 1, c_down)
 
-    model = nn.Sequential()
+    # the default-argument network (the only one the optimisation loop builds, models/networks.py:57) runs on the
+    # native sm_100a generator engine; any other configuration keeps the plain module-by-module evaluation
+    is_default = (num_input_channels == 3 and num_output_channels == 3 and list(num_channels_down) == [16, 32, 64, 128, 128]
+                  and list(num_channels_up) == [16, 32, 64, 128, 128] and list(num_channels_skip) == [4, 4, 4, 4, 4]
+                  and k_down == [3] * 5 and k_up == [3] * 5 and filter_skip_size == 1 and need_sigmoid and need_bias
+                  and pad == 'zero' and up_modes == ['bilinear'] * 5 and down_modes == ['stride'] * 5
+                  and act_fun == 'LeakyReLU' and need1x1_up)
+    model = NativeSkip() if is_default else nn.Sequential()
     fill_level(model, 0, num_input_channels)
     model.add(conv(num_channels_up[0], num_output_channels, 1, bias=need_bias, pad=pad))
     if need_sigmoid:

@@ -24,6 +24,26 @@ class FusedAdam(torch.optim.Optimizer):
                         foreach=None, capturable=False, differentiable=False, fused=True)
         super().__init__(params, defaults)
 
+    def zero_grad(self, set_to_none: bool = True):
+        """Gradients that live in the native generator's flat buffer are cleared with ONE memset and stay attached
+        (so the engine's pointer table stays valid); anything else follows torch's zero_grad."""
+        flats, rest = {}, []
+        for group in self.param_groups:
+            for p in group['params']:
+                flat = getattr(p, '_splice_flat_grad', None)
+                if flat is not None and p.grad is not None and p.grad is getattr(p, '_splice_grad_view', None):
+                    flats[id(flat)] = flat
+                else:
+                    rest.append(p)
+        for flat in flats.values():
+            flat.zero_()
+        for p in rest:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.detach_().zero_()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
