@@ -24,8 +24,7 @@ class _GenFn(torch.autograd.Function):
     parameter gradients are written by the engine as a side effect, the way fused optimisers consume them."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, anchor: torch.Tensor, module: "NativeSkip"):
-        keep = torch.is_grad_enabled() and anchor.requires_grad
+    def forward(ctx, x: torch.Tensor, anchor: torch.Tensor, module: "NativeSkip", keep: bool):
         out, slot, token = module._run_forward(x, keep)
         ctx.module, ctx.slot, ctx.token = module, slot, token
         return out
@@ -33,7 +32,7 @@ class _GenFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout: torch.Tensor):
         ctx.module._run_backward(gout, ctx.slot, ctx.token)
-        return None, None, None
+        return None, None, None, None
 
 
 class NativeSkip(nn.Sequential):
@@ -154,7 +153,8 @@ class NativeSkip(nn.Sequential):
 
     def forward(self, input):
         anchor = next(self.parameters())
-        return _GenFn.apply(input, anchor, self)
+        keep = torch.is_grad_enabled() and anchor.requires_grad   # (grad mode is off inside Function.forward)
+        return _GenFn.apply(input, anchor, self, keep)
 
     def forward_reference_ops(self, input):
         """The same tree evaluated module by module with torch ops (tests only: isolates engine bugs)."""
