@@ -311,7 +311,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, reference step schedule (every 75th step adds the "
                                "entire-image terms), crops 213-224 px", "pairs": world, "parallelism": f"{world} independent pair(s), 1/GPU",
                    "l2": "per-step working set (~0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
-                   "generator": "torch autograd + cuDNN (interim, round 1)"},
+                   "generator": "native fp32 SIMT conv/BN/LReLU kernels (splice_gen_*)"},
         "e2e": {"value": world * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": 4,
                 "steps": k_e2e, "note": "train.py loop body: pinned host crops -> device each step, loss.item() each step"},
         "gpu_launches": int(launches),
