@@ -27,15 +27,6 @@ struct InTf {               // per-channel transform applied to a raw tensor whe
     int lrelu;
 };
 
-enum DyMode : int { DY_PLAIN = 0, DY_BN_LRELU = 1, DY_BN = 2, DY_SIGMOID = 3 };
-struct DySrc {              // d(raw conv output) rebuilt from d(activated output)
-    const float* dA;
-    const float* y;         // raw conv output (DY_SIGMOID: the sigmoid output)
-    const float4* k;        // (mean, invstd, a, b)
-    const float2* m;        // (m1, m2) = (mean(dz), mean(dz * yhat))
-    int mode;
-};
-
 __device__ __forceinline__ float apply_tf(const InTf& tf, int c, float v) {
     if (tf.k) {
         const float4 k = tf.k[c];
@@ -44,22 +35,6 @@ __device__ __forceinline__ float apply_tf(const InTf& tf, int c, float v) {
     }
     return v;
 }
-__device__ __forceinline__ float dy_value(const DySrc& s, int c, size_t idx) {
-    const float g = s.dA[idx];
-    if (s.mode == DY_PLAIN) return g;
-    const float yv = s.y[idx];
-    if (s.mode == DY_SIGMOID) return g * yv * (1.f - yv);
-    const float4 k = s.k[c];
-    const float2 m = s.m[c];
-    float dz = g;
-    if (s.mode == DY_BN_LRELU) {
-        const float z = fmaf(k.z, yv, k.w);
-        if (!(z > 0.f)) dz *= LRELU;
-    }
-    const float yhat = (yv - k.x) * k.y;
-    return k.z * (dz - m.x - yhat * m.y);
-}
-
 // block-wide sums of NV values over 256 threads; result broadcast to every thread. red: >= 8*NV floats.
 template <int NV>
 __device__ __forceinline__ void block_reduce_vec(float (&v)[NV], float* red) {
@@ -83,89 +58,162 @@ __device__ __forceinline__ void block_reduce_vec(float (&v)[NV], float* red) {
 
 // -------------------------------------------------------------------------------------------------
 // forward convolution (+ producer BN/LeakyReLU on load, + bias, + optional sigmoid, + output statistics)
+//   one thread per output pixel (linear over N*Ho*Wo), CO_T output channels per thread, optional split over the
+//   input channels (blockIdx.z) for the low-resolution layers whose grids would otherwise not fill 148 SMs.
+//   Input taps come straight from global/L1 (neighbouring threads share them); weights are staged in smem.
 // -------------------------------------------------------------------------------------------------
+static constexpr int CONV_THREADS = 128;
+
 template <int K, int S, int CO_T>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf tf,
-                                                       const float* __restrict__ Wt, const float* __restrict__ bias, int Cout,
-                                                       float* __restrict__ y, int Ho, int Wo, int out_sigmoid,
-                                                       float* __restrict__ stats_part) {
-    constexpr int CI_T = 8, PAD = (K - 1) / 2;
-    constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-    __shared__ float s_in[CI_T][IH][IW + 1];
-    __shared__ __align__(16) float s_w[CI_T][K * K][CO_T];
-    __shared__ float red[8 * CO_T];
-    const int tiles_x = (Wo + TW - 1) / TW;
-    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
-    const int co0 = blockIdx.y * CO_T, n = blockIdx.z;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int oy = ty0 + ty, ox = tx0 + tx;
+__global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, InTf tf,
+                                                                const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                                int Cout, float* __restrict__ y, int Ho, int Wo, int out_sigmoid,
+                                                                float* __restrict__ stats_part, int splitK) {
+    constexpr int CI_C = 8, KK = K * K, PAD = (K - 1) / 2;
+    __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
+    __shared__ float2 s_ab[CI_C];
+    __shared__ float red[4 * CO_T];
+    const int P = N * Ho * Wo;
+    const int p = blockIdx.x * CONV_THREADS + threadIdx.x;
+    const bool active = p < P;
+    const int n = active ? p / (Ho * Wo) : 0, rem = active ? p % (Ho * Wo) : 0;
+    const int oy = rem / Wo, ox = rem % Wo;
+    const int co0 = blockIdx.y * CO_T;
+    const int cps = (Cin + splitK - 1) / splitK;
+    const int c_begin = blockIdx.z * cps, c_end = min(Cin, c_begin + cps);
+    const int iy0 = oy * S - PAD, ix0 = ox * S - PAD;
+    bool rok[K], cok[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        rok[k] = active && iy0 + k >= 0 && iy0 + k < Hin;
+        cok[k] = ix0 + k >= 0 && ix0 + k < Win;
+    }
     float acc[CO_T];
 #pragma unroll
     for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
 
-    for (int ci0 = 0; ci0 < Cin; ci0 += CI_T) {
-        for (int idx = threadIdx.x; idx < CI_T * IH * IW; idx += 256) {
-            const int ci = idx / (IH * IW), r = (idx / IW) % IH, c = idx % IW;
-            const int iy = ty0 * S - PAD + r, ix = tx0 * S - PAD + c;
-            float v = 0.f;
-            if (ci0 + ci < Cin && iy >= 0 && iy < Hin && ix >= 0 && ix < Win)
-                v = apply_tf(tf, ci0 + ci, x[((size_t)(n * Cin + ci0 + ci) * Hin + iy) * Win + ix]);
-            s_in[ci][r][c] = v;   // zero padding lives in the post-BN/activation domain, like the reference
+    for (int c0 = c_begin; c0 < c_end; c0 += CI_C) {
+        const int cn = min(CI_C, c_end - c0);
+        for (int idx = threadIdx.x; idx < CI_C * KK * CO_T; idx += CONV_THREADS) {
+            const int co = idx % CO_T, kk = (idx / CO_T) % KK, ci = idx / (CO_T * KK);
+            s_w[ci][kk][co] = (ci < cn && co0 + co < Cout) ? Wt[((size_t)(co0 + co) * Cin + c0 + ci) * KK + kk] : 0.f;
         }
-        for (int idx = threadIdx.x; idx < CI_T * K * K * CO_T; idx += 256) {
-            const int co = idx % CO_T, kk = (idx / CO_T) % (K * K), ci = idx / (CO_T * K * K);
-            s_w[ci][kk][co] = (co0 + co < Cout && ci0 + ci < Cin) ? Wt[((size_t)(co0 + co) * Cin + ci0 + ci) * K * K + kk] : 0.f;
+        if (threadIdx.x < CI_C) {
+            float2 ab = make_float2(1.f, 0.f);
+            if (tf.k && threadIdx.x < cn) { const float4 k4 = tf.k[c0 + threadIdx.x]; ab = make_float2(k4.z, k4.w); }
+            s_ab[threadIdx.x] = ab;
         }
         __syncthreads();
-        const int cmax = (Cin - ci0 < CI_T) ? Cin - ci0 : CI_T;
-        for (int ci = 0; ci < cmax; ++ci) {
+        for (int ci = 0; ci < cn; ++ci) {
+            const float* base = x + ((size_t)(n * Cin + c0 + ci) * Hin) * Win;
+            const float2 ab = s_ab[ci];
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky)
+            for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const float v = s_in[ci][ty * S + ky][tx * S + kx];
+                    float v = 0.f;
+                    if (rok[ky] && cok[kx]) {
+                        v = __ldg(base + (size_t)(iy0 + ky) * Win + ix0 + kx);
+                        if (tf.k) {
+                            v = fmaf(ab.x, v, ab.y);
+                            if (tf.lrelu && v < 0.f) v *= LRELU;
+                        }
+                    }   // zero padding lives in the post-BN/activation domain, like the reference
 #pragma unroll
                     for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v, s_w[ci][ky * K + kx][co], acc[co]);
                 }
+            }
         }
         __syncthreads();
     }
-    const bool valid = oy < Ho && ox < Wo;
+    if (splitK > 1) {   // partial sums; conv_finish_bn_kernel adds the bias and does the statistics
+        if (active) {
+            float* o = y + (size_t)blockIdx.z * ((size_t)N * Cout * Ho * Wo);
+#pragma unroll
+            for (int co = 0; co < CO_T; ++co)
+                if (co0 + co < Cout) o[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = acc[co];
+        }
+        return;
+    }
 #pragma unroll
     for (int co = 0; co < CO_T; ++co) {
         if (co0 + co < Cout) {
             float v = acc[co] + bias[co0 + co];
             if (out_sigmoid) v = 1.f / (1.f + __expf(-v));
             acc[co] = v;
-            if (valid) y[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = v;
+            if (active) y[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = v;
         }
     }
     if (stats_part) {
         // per-block (count, mean, M2) of each output channel: two block reductions, centred second pass
-        float v[CO_T];
-#pragma unroll
-        for (int co = 0; co < CO_T; ++co) v[co] = valid ? acc[co] : 0.f;
-        block_reduce_vec<CO_T>(v, red);
-        const int th = (Ho - ty0 < TH) ? Ho - ty0 : TH, tw = (Wo - tx0 < TW) ? Wo - tx0 : TW;
-        const float cnt = (float)(th * tw);
-        float mean[CO_T];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const float cnt = (float)min(CONV_THREADS, P - (int)blockIdx.x * CONV_THREADS);
+        float mean[CO_T], m2[CO_T];
 #pragma unroll
         for (int co = 0; co < CO_T; ++co) {
-            mean[co] = v[co] / cnt;
-            const float d = acc[co] - mean[co];
-            v[co] = valid ? d * d : 0.f;
+            const float sv = warp_sum(active ? acc[co] : 0.f);
+            if (lane == 0) red[w * CO_T + co] = sv;
         }
-        block_reduce_vec<CO_T>(v, red);
-        if (threadIdx.x < CO_T && co0 + threadIdx.x < Cout) {
-            const int co = threadIdx.x;
-            const size_t pb = (size_t)n * gridDim.x + blockIdx.x;
-            float* o = stats_part + (pb * Cout + co0 + co) * 3;
-            // mean[]/v[] are per-thread register arrays indexed by a runtime value: spill-free form below
-            float mco = 0.f, vco = 0.f;
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < CO_T; ++j)
-                if (j == co) { mco = mean[j]; vco = v[j]; }
-            o[0] = cnt; o[1] = mco; o[2] = vco;
+        for (int co = 0; co < CO_T; ++co) mean[co] = (red[co] + red[CO_T + co] + red[2 * CO_T + co] + red[3 * CO_T + co]) / cnt;
+        __syncthreads();
+#pragma unroll
+        for (int co = 0; co < CO_T; ++co) {
+            const float d = acc[co] - mean[co];
+            const float sv = warp_sum(active ? d * d : 0.f);
+            if (lane == 0) red[w * CO_T + co] = sv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int co = 0; co < CO_T; ++co) m2[co] = red[co] + red[CO_T + co] + red[2 * CO_T + co] + red[3 * CO_T + co];
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int co = 0; co < CO_T; ++co)
+                if (co0 + co < Cout) {
+                    float* o = stats_part + ((size_t)blockIdx.x * Cout + co0 + co) * 3;
+                    o[0] = cnt; o[1] = mean[co]; o[2] = m2[co];
+                }
+        }
+    }
+}
+
+// split-K epilogue: y = bias + sum of partials, and the BatchNorm statistics / constants of the channel in one go
+// (one block per channel; only used by the low-resolution layers, N*H*W <= a few thousand)
+__global__ void __launch_bounds__(256) conv_finish_bn_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
+                                                             float* __restrict__ y, int N, int C, int HW,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                             float4* __restrict__ konst, float* running_mean, float* running_var,
+                                                             long long* nbt, float momentum) {
+    __shared__ float red[8];
+    const int c = blockIdx.x, count = N * HW;
+    const size_t total = (size_t)N * C * HW;
+    const float b = bias[c];
+    float a[1] = {0.f};
+    for (int e = threadIdx.x; e < count; e += 256) {
+        const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
+        float v = b;
+        for (int k = 0; k < splitK; ++k) v += part[(size_t)k * total + idx];
+        y[idx] = v;
+        a[0] += v;
+    }
+    block_reduce_vec<1>(a, red);
+    const float mean = a[0] / count;
+    a[0] = 0.f;
+    for (int e = threadIdx.x; e < count; e += 256) {   // each thread re-reads exactly what it wrote
+        const float d = y[((size_t)(e / HW) * C + c) * HW + (e % HW)] - mean;
+        a[0] += d * d;
+    }
+    block_reduce_vec<1>(a, red);
+    if (threadIdx.x == 0) {
+        const float var = a[0] / count;
+        const float invstd = rsqrtf(var + eps);
+        const float g = gamma[c] * invstd;
+        konst[c] = make_float4(mean, invstd, g, beta[c] - mean * g);
+        if (running_mean) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (count > 1 ? a[0] / (count - 1) : var);
+            if (c == 0 && nbt) *nbt += 1;
         }
     }
 }
@@ -304,51 +352,101 @@ __global__ void __launch_bounds__(32) bn_bwd_finalize_kernel(const float* __rest
     }
 }
 
-// d(transformed conv input) [N,Cin,Hin,Win] (= or +=)  from  d(conv output) rebuilt on the fly
+// dA <- d(raw conv output) in place: dy = a * (dz - m1 - yhat * m2), dz = dA * LeakyReLU'(z)  (large layers)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ y,
+                                                           const float4* __restrict__ konst, const float2* __restrict__ m, int lrelu,
+                                                           int C, int HW, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int c = (i / HW) % C;
+        const float4 k = konst[c];
+        const float2 mm = m[c];
+        const float yv = y[i];
+        float dz = dA[i];
+        if (lrelu && !(fmaf(k.z, yv, k.w) > 0.f)) dz *= LRELU;
+        dA[i] = k.z * (dz - mm.x - (yv - k.x) * k.y * mm.y);
+    }
+}
+// the whole BatchNorm backward of one channel in one block (small layers: N*H*W <= 8192):
+// reduce, dgamma/dbeta accumulation, and the in-place dA -> dy rewrite
+__global__ void __launch_bounds__(256) bn_bwd_small_kernel(float* __restrict__ dA, const float* __restrict__ y,
+                                                           const float4* __restrict__ konst, int lrelu, int N, int C, int HW,
+                                                           float* dgamma, float* dbeta) {
+    __shared__ float red[16];
+    const int c = blockIdx.x, count = N * HW;
+    const float4 k = konst[c];
+    float a[2] = {0.f, 0.f};
+    for (int e = threadIdx.x; e < count; e += 256) {
+        const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
+        const float yv = y[idx];
+        float dz = dA[idx];
+        if (lrelu && !(fmaf(k.z, yv, k.w) > 0.f)) dz *= LRELU;
+        a[0] += dz;
+        a[1] += dz * (yv - k.x) * k.y;
+    }
+    block_reduce_vec<2>(a, red);
+    if (threadIdx.x == 0) {
+        if (dgamma) dgamma[c] += a[1];
+        if (dbeta) dbeta[c] += a[0];
+    }
+    const float m1 = a[0] / count, m2 = a[1] / count;
+    for (int e = threadIdx.x; e < count; e += 256) {
+        const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
+        const float yv = y[idx];
+        float dz = dA[idx];
+        if (lrelu && !(fmaf(k.z, yv, k.w) > 0.f)) dz *= LRELU;
+        dA[idx] = k.z * (dz - m1 - (yv - k.x) * k.y * m2);
+    }
+}
+// d(sigmoid output) -> d(pre-sigmoid) for the final 1x1 conv
+__global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                          float* __restrict__ dy, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const float o = out[i];
+        dy[i] = dout[i] * o * (1.f - o);
+    }
+}
+
+// d(transformed conv input) [N,Cin,Hin,Win] from dy [N,Cout,Ho,Wo]: one thread per input pixel, CI_T input channels
+// per thread, optional split over the output channels (blockIdx.z) for the low-resolution layers
 template <int K, int S, int CI_T>
-__global__ void __launch_bounds__(256) conv_dgrad_kernel(DySrc src, int Cout, int Ho, int Wo, const float* __restrict__ Wt, int Cin,
-                                                         float* __restrict__ dX, int Hin, int Win, int accumulate) {
-    constexpr int CO_C = 8, PAD = (K - 1) / 2;
-    constexpr int DH = (TH + K - 2) / S + 2, DW = (TW + K - 2) / S + 2;
-    __shared__ float s_dy[CO_C][DH][DW + 1];
-    __shared__ __align__(16) float s_w[CO_C][K * K][CI_T];
-    const int tiles_x = (Win + TW - 1) / TW;
-    const int iy0 = (blockIdx.x / tiles_x) * TH, ix0 = (blockIdx.x % tiles_x) * TW;
-    const int ci0 = blockIdx.y * CI_T, n = blockIdx.z;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int iy = iy0 + ty, ix = ix0 + tx;
-    // first output row/col that any pixel of this tile can touch (floor division, arguments may be negative)
-    const int oyb = (iy0 + PAD - (K - 1) + 4 * S) / S - 4, oxb = (ix0 + PAD - (K - 1) + 4 * S) / S - 4;
+__global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo,
+                                                                  const float* __restrict__ Wt, int Cin, float* __restrict__ dX,
+                                                                  int Hin, int Win, int accumulate, int splitK) {
+    constexpr int CO_C = 8, KK = K * K, PAD = (K - 1) / 2;
+    __shared__ __align__(16) float s_w[CO_C][KK][CI_T];
+    const int P = N * Hin * Win;
+    const int p = blockIdx.x * CONV_THREADS + threadIdx.x;
+    const bool active = p < P;
+    const int n = active ? p / (Hin * Win) : 0, rem = active ? p % (Hin * Win) : 0;
+    const int iy = rem / Win, ix = rem % Win;
+    const int ci0 = blockIdx.y * CI_T;
+    const int cps = (Cout + splitK - 1) / splitK;
+    const int c_begin = blockIdx.z * cps, c_end = min(Cout, c_begin + cps);
+    int oyk[K], oxk[K];   // output row / column reached through tap k, or -1
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int ty = iy + PAD - k, tx = ix + PAD - k;
+        oyk[k] = (active && ty >= 0 && ty % S == 0 && ty / S < Ho) ? ty / S : -1;
+        oxk[k] = (tx >= 0 && tx % S == 0 && tx / S < Wo) ? tx / S : -1;
+    }
     float acc[CI_T];
 #pragma unroll
     for (int i = 0; i < CI_T; ++i) acc[i] = 0.f;
-    for (int co0 = 0; co0 < Cout; co0 += CO_C) {
-        for (int idx = threadIdx.x; idx < CO_C * DH * DW; idx += 256) {
-            const int co = idx / (DH * DW), r = (idx / DW) % DH, c = idx % DW;
-            const int oy = oyb + r, ox = oxb + c;
-            float v = 0.f;
-            if (co0 + co < Cout && oy >= 0 && oy < Ho && ox >= 0 && ox < Wo)
-                v = dy_value(src, co0 + co, ((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox);
-            s_dy[co][r][c] = v;
-        }
-        for (int idx = threadIdx.x; idx < CO_C * K * K * CI_T; idx += 256) {
-            const int ci = idx % CI_T, kk = (idx / CI_T) % (K * K), co = idx / (CI_T * K * K);
-            s_w[co][kk][ci] = (co0 + co < Cout && ci0 + ci < Cin) ? Wt[((size_t)(co0 + co) * Cin + ci0 + ci) * K * K + kk] : 0.f;
+    for (int c0 = c_begin; c0 < c_end; c0 += CO_C) {
+        const int cn = min(CO_C, c_end - c0);
+        for (int idx = threadIdx.x; idx < CO_C * KK * CI_T; idx += CONV_THREADS) {
+            const int ci = idx % CI_T, kk = (idx / CI_T) % KK, co = idx / (CI_T * KK);
+            s_w[co][kk][ci] = (co < cn && ci0 + ci < Cin) ? Wt[((size_t)(c0 + co) * Cin + ci0 + ci) * KK + kk] : 0.f;
         }
         __syncthreads();
-        const int cmax = (Cout - co0 < CO_C) ? Cout - co0 : CO_C;
-        for (int co = 0; co < cmax; ++co) {
+        for (int co = 0; co < cn; ++co) {
+            const float* base = dy + ((size_t)(n * Cout + c0 + co) * Ho) * Wo;
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                const int t = iy + PAD - ky + 4 * S;          // oy * S = iy + PAD - ky
-                if (S > 1 && (t % S) != 0) continue;           // warp-uniform (iy is)
-                const int r = t / S - 4 - oyb;
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const int u = ix + PAD - kx + 4 * S;
-                    const bool ok = (S == 1) || (u % S) == 0;
-                    const int c = u / S - 4 - oxb;
-                    const float v = ok ? s_dy[co][r][c] : 0.f;
+                    float v = 0.f;
+                    if (oyk[ky] >= 0 && oxk[kx] >= 0) v = __ldg(base + (size_t)oyk[ky] * Wo + oxk[kx]);
 #pragma unroll
                     for (int ci = 0; ci < CI_T; ++ci) acc[ci] = fmaf(v, s_w[co][ky * K + kx][ci], acc[ci]);
                 }
@@ -356,13 +454,22 @@ __global__ void __launch_bounds__(256) conv_dgrad_kernel(DySrc src, int Cout, in
         }
         __syncthreads();
     }
-    if (iy < Hin && ix < Win) {
+    if (!active) return;
+    float* o = dX + (splitK > 1 ? (size_t)blockIdx.z * ((size_t)N * Cin * Hin * Win) : 0);
 #pragma unroll
-        for (int ci = 0; ci < CI_T; ++ci)
-            if (ci0 + ci < Cin) {
-                float* o = dX + ((size_t)(n * Cin + ci0 + ci) * Hin + iy) * Win + ix;
-                *o = accumulate ? *o + acc[ci] : acc[ci];
-            }
+    for (int ci = 0; ci < CI_T; ++ci)
+        if (ci0 + ci < Cin) {
+            float* q = o + ((size_t)(n * Cin + ci0 + ci) * Hin + iy) * Win + ix;
+            *q = (accumulate && splitK == 1) ? *q + acc[ci] : acc[ci];
+        }
+}
+// dst (=|+=) sum over the split partials
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splitK, size_t total,
+                                                           float* __restrict__ dst, int accumulate) {
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        float v = accumulate ? dst[i] : 0.f;
+        for (int k = 0; k < splitK; ++k) v += part[(size_t)k * total + i];
+        dst[i] = v;
     }
 }
 
@@ -375,8 +482,9 @@ constexpr int wgrad_smem_floats() {
     return a > b ? a : b;
 }
 template <int K, int S>
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf tf, DySrc src,
-                                                         int Cout, int Ho, int Wo, int N, float* __restrict__ part) {
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf tf,
+                                                         const float* __restrict__ dy, int Cout, int Ho, int Wo, int N,
+                                                         float* __restrict__ part) {
     constexpr int CO_T = 16, CI_T = 8, PAD = (K - 1) / 2, KK = K * K;
     constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K, IWP = IW + 1;
     constexpr int SX = CI_T * IH * IWP;
@@ -411,7 +519,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
             const int c = idx / (TH * TW), r = (idx / TW) % TH, q = idx % TW;
             const int oy = ty0 + r, ox = tx0 + q;
             float v = 0.f;
-            if (co0 + c < Cout && oy < Ho && ox < Wo) v = dy_value(src, co0 + c, ((size_t)(n * Cout + co0 + c) * Ho + oy) * Wo + ox);
+            if (co0 + c < Cout && oy < Ho && ox < Wo) v = dy[((size_t)(n * Cout + co0 + c) * Ho + oy) * Wo + ox];
             s_dy[c][r][q] = v;
         }
         __syncthreads();
@@ -474,7 +582,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 // adjoint of cat_build for the skip branch: d(s activated) = d(cat)[:, :Cs] placed at the crop offset, zero elsewhere
-__global__ void __launch_bounds__(256) cat_bwd_skip_kernel(DySrc src, int C, int H, int W, int Cs, int Hs, int Ws, int offy,
+__global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const float* __restrict__ dcat, int C, int H, int W, int Cs, int Hs, int Ws, int offy,
                                                            int offx, float* __restrict__ dS) {
     const size_t total = (size_t)gridDim.z * Cs * Hs * Ws;
     const int n = blockIdx.z;
@@ -482,13 +590,13 @@ __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(DySrc src, int C, int
         const int c = i / ((size_t)Hs * Ws), y = (i / Ws) % Hs, x = i % Ws;
         const int cy = y - offy, cx = x - offx;
         float v = 0.f;
-        if (cy >= 0 && cy < H && cx >= 0 && cx < W) v = dy_value(src, c, ((size_t)(n * C + c) * H + cy) * W + cx);
+        if (cy >= 0 && cy < H && cx >= 0 && cx < W) v = dcat[((size_t)(n * C + c) * H + cy) * W + cx];
         dS[(size_t)n * Cs * Hs * Ws + i] = v;
     }
     (void)total;
 }
 // adjoint of the bilinear x2 up-sampling (+ crop): d(u activated)[n,cu,yu,xu] = sum over the <= 4x4 fine pixels that read it
-__global__ void __launch_bounds__(256) cat_bwd_up_kernel(DySrc src, int C, int H, int W, int Cs, int Cu, int Hu, int Wu, int offy,
+__global__ void __launch_bounds__(256) cat_bwd_up_kernel(const float* __restrict__ dcat, int C, int H, int W, int Cs, int Cu, int Hu, int Wu, int offy,
                                                          int offx, float* __restrict__ dU) {
     const int n = blockIdx.z;
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < (size_t)Cu * Hu * Wu; i += (size_t)gridDim.x * 256) {
@@ -510,7 +618,7 @@ __global__ void __launch_bounds__(256) cat_bwd_up_kernel(DySrc src, int C, int H
                 const float wx = (x0 == xu ? 1.f - lx : 0.f) + (x1 == xu ? lx : 0.f);
                 const int cx = X - offx;
                 if (wx == 0.f || cx < 0 || cx >= W) continue;
-                acc += wy * wx * dy_value(src, Cs + cu, ((size_t)(n * C + Cs + cu) * H + cy) * W + cx);
+                acc += wy * wx * dcat[((size_t)(n * C + Cs + cu) * H + cy) * W + cx];
             }
         }
         dU[(size_t)n * Cu * Hu * Wu + i] = acc;
@@ -520,32 +628,89 @@ __global__ void __launch_bounds__(256) cat_bwd_up_kernel(DySrc src, int C, int H
 // -------------------------------------------------------------------------------------------------
 // host: launch helpers
 // -------------------------------------------------------------------------------------------------
+static constexpr int TARGET_BLOCKS = 296;          // two CTAs per SM on 148 SMs
+static constexpr size_t SPLIT_FLOATS = 8u << 20;   // scratch for split partial sums (floats)
+static constexpr size_t WGRAD_FLOATS = 8u << 20;   // scratch for weight-gradient partials (floats)
+
+// channel tile (4 / 8 / 16) and split factor that bring a layer's grid to >= TARGET_BLOCKS where possible
+static void pick_tiling(int P, int Cfast, int Cslow, size_t out_elems, int* ct, int* split) {
+    const int pb = ceil_div(P, CONV_THREADS);
+    int t = Cfast <= 4 ? 4 : 16;
+    if (t == 16 && pb * ceil_div(Cfast, 16) < TARGET_BLOCKS && Cfast >= 8) t = 8;
+    if (t == 8 && pb * ceil_div(Cfast, 8) < TARGET_BLOCKS) t = 4;
+    int sk = 1;
+    const int blocks = pb * ceil_div(Cfast, t);
+    if (blocks < TARGET_BLOCKS) {
+        sk = ceil_div(TARGET_BLOCKS, blocks);
+        const int max_sk = Cslow / 8 > 0 ? Cslow / 8 : 1;          // at least 8 reduction channels per split
+        if (sk > max_sk) sk = max_sk;
+        if (sk > 16) sk = 16;
+        while (sk > 1 && (size_t)sk * out_elems > SPLIT_FLOATS) --sk;
+    }
+    *ct = t; *split = sk;
+}
+
+struct BnOut {                 // where the BatchNorm constants / running statistics of a conv's output go
+    const float *gamma, *beta;
+    float4* konst;
+    float *rmean, *rvar;
+    long long* nbt;
+};
+
 static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin, int Win, InTf tf, const float* Wt,
-                           const float* bias, int Cout, float* y, int Ho, int Wo, int sigmoid, float* stats, cudaStream_t st) {
-    const int tiles = ceil_div(Ho, TH) * ceil_div(Wo, TW);
-    const bool small = Cout <= 4;
-    dim3 grid(tiles, ceil_div(Cout, small ? 4 : 16), N);
-#define CF(KK, SS, CT) conv_fwd_kernel<KK, SS, CT><<<grid, 256, 0, st>>>(x, Cin, Hin, Win, tf, Wt, bias, Cout, y, Ho, Wo, sigmoid, stats)
-    if (K == 1 && S == 1) { if (small) CF(1, 1, 4); else CF(1, 1, 16); }
-    else if (K == 3 && S == 1) { if (small) CF(3, 1, 4); else CF(3, 1, 16); }
-    else if (K == 3 && S == 2) { if (small) CF(3, 2, 4); else CF(3, 2, 16); }
+                           const float* bias, int Cout, float* y, int Ho, int Wo, int sigmoid, const BnOut* bn, float* stats_part,
+                           float* split_part, cudaStream_t st) {
+    const int P = N * Ho * Wo;
+    int ct, sk;
+    pick_tiling(P, Cout, Cin, (size_t)N * Cout * Ho * Wo, &ct, &sk);
+    if (!bn) sk = 1;   // the final conv has no BatchNorm epilogue to fold the split reduction into
+    dim3 grid(ceil_div(P, CONV_THREADS), ceil_div(Cout, ct), sk);
+    float* dst = sk > 1 ? split_part : y;
+    float* stats = (sk > 1 || !bn) ? nullptr : stats_part;
+#define CF(KK, SS, CT) conv_fwd_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, sigmoid, stats, sk)
+#define CF3(KK, SS) do { if (ct == 4) CF(KK, SS, 4); else if (ct == 8) CF(KK, SS, 8); else CF(KK, SS, 16); } while (0)
+    if (K == 1 && S == 1) CF3(1, 1);
+    else if (K == 3 && S == 1) CF3(3, 1);
+    else if (K == 3 && S == 2) CF3(3, 2);
     else { set_error("generator: unsupported conv k=%d stride=%d", K, S); return SPLICE_ERR_UNSUPPORTED; }
+#undef CF3
 #undef CF
+    SPLICE_LAUNCH_CHECK();
+    if (!bn) return SPLICE_OK;
+    const float eps = 1e-5f, mom = 0.1f;
+    if (sk > 1) {
+        conv_finish_bn_kernel<<<Cout, 256, 0, st>>>(split_part, sk, bias, y, N, Cout, Ho * Wo, bn->gamma, bn->beta, eps, bn->konst,
+                                                    bn->rmean, bn->rvar, bn->nbt, mom);
+    } else {
+        bn_finalize_kernel<<<Cout, 32, 0, st>>>(stats_part, (int)grid.x, Cout, bn->gamma, bn->beta, eps, bn->konst, bn->rmean,
+                                                bn->rvar, bn->nbt, mom);
+    }
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
-static int launch_conv_dgrad(int K, int S, DySrc src, int N, int Cout, int Ho, int Wo, const float* Wt, int Cin, float* dX, int Hin,
-                             int Win, int accumulate, cudaStream_t st) {
-    const int tiles = ceil_div(Hin, TH) * ceil_div(Win, TW);
-    const bool small = Cin <= 4;
-    dim3 grid(tiles, ceil_div(Cin, small ? 4 : 16), N);
-#define DG(KK, SS, CT) conv_dgrad_kernel<KK, SS, CT><<<grid, 256, 0, st>>>(src, Cout, Ho, Wo, Wt, Cin, dX, Hin, Win, accumulate)
-    if (K == 1 && S == 1) { if (small) DG(1, 1, 4); else DG(1, 1, 16); }
-    else if (K == 3 && S == 1) { if (small) DG(3, 1, 4); else DG(3, 1, 16); }
-    else if (K == 3 && S == 2) { if (small) DG(3, 2, 4); else DG(3, 2, 16); }
+
+static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int Ho, int Wo, const float* Wt, int Cin, float* dX,
+                             int Hin, int Win, int accumulate, float* split_part, cudaStream_t st) {
+    const int P = N * Hin * Win;
+    int ct, sk;
+    const size_t total = (size_t)N * Cin * Hin * Win;
+    pick_tiling(P, Cin, Cout, total, &ct, &sk);
+    dim3 grid(ceil_div(P, CONV_THREADS), ceil_div(Cin, ct), sk);
+    float* dst = sk > 1 ? split_part : dX;
+#define DG(KK, SS, CT) conv_dgrad_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(dy, N, Cout, Ho, Wo, Wt, Cin, dst, Hin, Win, accumulate, sk)
+#define DG3(KK, SS) do { if (ct == 4) DG(KK, SS, 4); else if (ct == 8) DG(KK, SS, 8); else DG(KK, SS, 16); } while (0)
+    if (K == 1 && S == 1) DG3(1, 1);
+    else if (K == 3 && S == 1) DG3(3, 1);
+    else if (K == 3 && S == 2) DG3(3, 2);
     else { set_error("generator: unsupported conv k=%d stride=%d", K, S); return SPLICE_ERR_UNSUPPORTED; }
+#undef DG3
 #undef DG
     SPLICE_LAUNCH_CHECK();
+    if (sk > 1) {
+        const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        sum_partials_kernel<<<blocks, 256, 0, st>>>(split_part, sk, total, dX, accumulate);
+        SPLICE_LAUNCH_CHECK();
+    }
     return SPLICE_OK;
 }
 
@@ -613,6 +778,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     }
     plan((size_t)N * 3 * H * W * 4);  // x copy
     plan((size_t)N * 3 * H * W * 4);  // out copy
+    plan((size_t)N * 3 * H * W * 4);  // d(pre-sigmoid)
     if (off > s.pool_bytes) {
         SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
         cudaFree(s.pool);
@@ -634,6 +800,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     }
     s.x_copy = (float*)nx();
     s.out = (float*)nx();
+    s.dfin = (float*)nx();
     s.N = N; s.H = H; s.W = W;
     s.valid = false;
     return SPLICE_OK;
@@ -651,25 +818,23 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
     SPLICE_REQUIRE(x && out && N > 0 && H > 0 && W > 0, "generator: bad input");
     Slot& s = slots_[slot];
     GRC(configure(s, N, H, W));
-    // scratch: statistics partials of the largest layer: N * tiles(H,W) * Cmax(132) * 3 floats; wgrad partials (backward)
-    const size_t tiles0 = (size_t)ceil_div(H, TH) * ceil_div(W, TW);
-    const size_t wg = (size_t)32 * (132 * 128 * 9 + 128);
-    GRC(ensure_scratch((N * tiles0 * 132 * 3 + wg) * sizeof(float) + 4096));
+    // scratch = [statistics partials | split partial sums | weight-gradient partials]
+    const size_t stats_floats = (size_t)ceil_div(N * H * W, CONV_THREADS) * 132 * 3 + (size_t)N * ceil_div(H, TH) * ceil_div(W, TW) * 132 * 3;
+    GRC(ensure_scratch((stats_floats + SPLIT_FLOATS + WGRAD_FLOATS) * sizeof(float) + 4096));
+    s.stats_floats = stats_floats;
     float* part = static_cast<float*>(scratch_);
+    float* split = part + stats_floats;
     const float eps = 1e-5f, mom = 0.1f;
 
-    auto bn_fin = [&](const Bn& b, int nparts, float4* k) -> int {
-        bn_finalize_kernel<<<b.c, 32, 0, st>>>(part, nparts, b.c, p.param[b.pg], p.param[b.pb], eps, k,
-                                               update_running ? p.running_mean[b.idx] : nullptr,
-                                               update_running ? p.running_var[b.idx] : nullptr,
-                                               update_running ? p.num_batches_tracked[b.idx] : nullptr, mom);
-        SPLICE_LAUNCH_CHECK();
-        return SPLICE_OK;
+    auto bn_out = [&](const Bn& b, float4* k) {
+        return BnOut{p.param[b.pg], p.param[b.pb], k, update_running ? p.running_mean[b.idx] : nullptr,
+                     update_running ? p.running_var[b.idx] : nullptr, update_running ? p.num_batches_tracked[b.idx] : nullptr};
     };
     auto conv_bn = [&](const Conv& c, const Bn& b, const float* in, int hin, int win, InTf tf, float* y, int ho, int wo,
                        float4* k) -> int {
-        GRC(launch_conv_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, p.param[c.pw], p.param[c.pb], c.cout, y, ho, wo, 0, part, st));
-        return bn_fin(b, N * ceil_div(ho, TH) * ceil_div(wo, TW), k);
+        const BnOut bo = bn_out(b, k);
+        return launch_conv_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, p.param[c.pw], p.param[c.pb], c.cout, y, ho, wo, 0, &bo, part,
+                               split, st);
     };
 
     // keep a private copy of the input: the caller's tensor may be freed before backward() (wgrad of scale 0 reads it)
@@ -703,12 +868,16 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
         cat_build_kernel<<<grid, 256, 0, st>>>(b.s_raw, 4, b.h, b.w, InTf{b.k_s, 1}, oys, oxs, u, c.cdeep, hu, wu, tf_u, oyu, oxu,
                                                b.cat, th, tw, part);
         SPLICE_LAUNCH_CHECK();
-        GRC(bn_fin(c.bcat, N * ceil_div(th, TH) * ceil_div(tw, TW), b.k_cat));
+        {
+            const BnOut bo = bn_out(c.bcat, b.k_cat);
+            bn_finalize_kernel<<<C, 32, 0, st>>>(part, N * (int)grid.x, C, bo.gamma, bo.beta, eps, bo.konst, bo.rmean, bo.rvar, bo.nbt, mom);
+            SPLICE_LAUNCH_CHECK();
+        }
         GRC(conv_bn(c.c1, c.bc1, b.cat, th, tw, InTf{b.k_cat, 0}, b.c1_raw, th, tw, b.k_c1));
         GRC(conv_bn(c.c2, c.bc2, b.c1_raw, th, tw, InTf{b.k_c1, 1}, b.c2_raw, th, tw, b.k_c2));
     }
     GRC(launch_conv_fwd(1, 1, s.sb[0].c2_raw, N, final_.cin, H, W, InTf{s.sb[0].k_c2, 1}, p.param[final_.pw], p.param[final_.pb], 3,
-                        s.out, H, W, 1, nullptr, st));
+                        s.out, H, W, 1, nullptr, nullptr, nullptr, st));
     SPLICE_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     s.valid = keep;
     return SPLICE_OK;
@@ -720,22 +889,36 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
     SPLICE_REQUIRE(s.pool && s.valid, "generator backward: slot %d holds no kept forward pass", slot);
     SPLICE_REQUIRE(dout, "generator backward: null gradient");
     const int N = s.N, H = s.H, W = s.W;
-    const size_t tiles0 = (size_t)ceil_div(H, TH) * ceil_div(W, TW);
     float* part = static_cast<float*>(scratch_);
-    float* wpart = part + N * tiles0 * 132 * 3;
+    float* split = part + s.stats_floats;
+    float* wpart = split + SPLIT_FLOATS;
 
-    auto bn_bwd = [&](const Bn& b, const float* dA, const float* y, const float4* k, int lrelu, int hw_h, int hw_w, float2* m) -> int {
-        const int HW = hw_h * hw_w;
+    // BatchNorm(+LeakyReLU) backward of one layer: afterwards dA holds d(raw conv output)
+    auto bn_bwd = [&](const Bn& b, float* dA, const float* y, const float4* k, int lrelu, int hh, int ww, float2* m) -> int {
+        const int HW = hh * ww;
+        if ((size_t)N * HW <= 8192) {
+            bn_bwd_small_kernel<<<b.c, 256, 0, st>>>(dA, y, k, lrelu, N, b.c, HW, p.grad[b.pg], p.grad[b.pb]);
+            SPLICE_LAUNCH_CHECK();
+            return SPLICE_OK;
+        }
         dim3 grid(ceil_div(HW, 2048), b.c, N);
         bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dA, y, k, lrelu, b.c, HW, part);
         SPLICE_LAUNCH_CHECK();
         bn_bwd_finalize_kernel<<<b.c, 32, 0, st>>>(part, N * (int)grid.x, b.c, (double)N * HW, p.grad[b.pg], p.grad[b.pb], m);
         SPLICE_LAUNCH_CHECK();
+        const size_t total = (size_t)N * b.c * HW;
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dA, y, k, m, lrelu, b.c, HW, total);
+        SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
-    auto wgrad = [&](const Conv& c, const float* in, int hin, int win, InTf tf, DySrc src, int ho, int wo) -> int {
+    auto wgrad = [&](const Conv& c, const float* in, int hin, int win, InTf tf, const float* dy, int ho, int wo) -> int {
         const int ntiles = N * ceil_div(ho, TH) * ceil_div(wo, TW);
-        const int chunks = ntiles < 32 ? ntiles : 32;
+        const size_t nW = (size_t)c.cout * c.cin * c.k * c.k;
+        size_t cap = WGRAD_FLOATS / (nW + c.cout);
+        if (cap > 256) cap = 256;
+        if (cap < 1) cap = 1;
+        const int chunks = ntiles < (int)cap ? ntiles : (int)cap;
         dim3 grid(chunks, ceil_div(c.cout, 16) * ceil_div(c.cin, 8));
         static bool attr = false;
         if (!attr) {
@@ -745,23 +928,27 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
             attr = true;
         }
         if (c.k == 1 && c.stride == 1)
-            conv_wgrad_kernel<1, 1><<<grid, 256, wgrad_smem_floats<1, 1>() * 4, st>>>(in, c.cin, hin, win, tf, src, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<1, 1><<<grid, 256, wgrad_smem_floats<1, 1>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         else if (c.k == 3 && c.stride == 1)
-            conv_wgrad_kernel<3, 1><<<grid, 256, wgrad_smem_floats<3, 1>() * 4, st>>>(in, c.cin, hin, win, tf, src, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<3, 1><<<grid, 256, wgrad_smem_floats<3, 1>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         else
-            conv_wgrad_kernel<3, 2><<<grid, 256, wgrad_smem_floats<3, 2>() * 4, st>>>(in, c.cin, hin, win, tf, src, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<3, 2><<<grid, 256, wgrad_smem_floats<3, 2>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         SPLICE_LAUNCH_CHECK();
-        const size_t nW = (size_t)c.cout * c.cin * c.k * c.k;
         wgrad_reduce_kernel<<<ceil_div((int)(nW + c.cout), 256), 256, 0, st>>>(wpart, chunks, nW, c.cout, p.grad[c.pw], p.grad[c.pb]);
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
+    auto dgrad = [&](const Conv& c, const float* dy, int ho, int wo, float* dX, int hin, int win, int accumulate) -> int {
+        return launch_conv_dgrad(c.k, c.stride, dy, N, c.cout, ho, wo, p.param[c.pw], c.cin, dX, hin, win, accumulate, split, st);
+    };
 
     // final 1x1 conv + sigmoid
     {
-        DySrc src{dout, s.out, nullptr, nullptr, DY_SIGMOID};
-        GRC(wgrad(final_, s.sb[0].c2_raw, H, W, InTf{s.sb[0].k_c2, 1}, src, H, W));
-        GRC(launch_conv_dgrad(1, 1, src, N, 3, H, W, p.param[final_.pw], final_.cin, s.sb[0].dA_c2, H, W, 0, st));
+        const size_t total = (size_t)N * 3 * H * W;
+        sigmoid_bwd_kernel<<<(int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, st>>>(dout, s.out, s.dfin, total);
+        SPLICE_LAUNCH_CHECK();
+        GRC(wgrad(final_, s.sb[0].c2_raw, H, W, InTf{s.sb[0].k_c2, 1}, s.dfin, H, W));
+        GRC(dgrad(final_, s.dfin, H, W, s.sb[0].dA_c2, H, W, 0));
     }
     // up path, top to bottom
     for (int i = 0; i < GEN_SCALES; ++i) {
@@ -769,26 +956,23 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
         ScaleBuf& b = s.sb[i];
         const int h = b.h, w = b.w;
         GRC(bn_bwd(c.bc2, b.dA_c2, b.c2_raw, b.k_c2, 1, h, w, b.m_c2));
-        DySrc s_c2{b.dA_c2, b.c2_raw, b.k_c2, b.m_c2, DY_BN_LRELU};
-        GRC(wgrad(c.c2, b.c1_raw, h, w, InTf{b.k_c1, 1}, s_c2, h, w));
-        GRC(launch_conv_dgrad(1, 1, s_c2, N, c.c2.cout, h, w, p.param[c.c2.pw], c.c2.cin, b.dA_c1, h, w, 0, st));
+        GRC(wgrad(c.c2, b.c1_raw, h, w, InTf{b.k_c1, 1}, b.dA_c2, h, w));
+        GRC(dgrad(c.c2, b.dA_c2, h, w, b.dA_c1, h, w, 0));
 
         GRC(bn_bwd(c.bc1, b.dA_c1, b.c1_raw, b.k_c1, 1, h, w, b.m_c1));
-        DySrc s_c1{b.dA_c1, b.c1_raw, b.k_c1, b.m_c1, DY_BN_LRELU};
-        GRC(wgrad(c.c1, b.cat, h, w, InTf{b.k_cat, 0}, s_c1, h, w));
-        GRC(launch_conv_dgrad(3, 1, s_c1, N, c.c1.cout, h, w, p.param[c.c1.pw], c.c1.cin, b.dcat, h, w, 0, st));
+        GRC(wgrad(c.c1, b.cat, h, w, InTf{b.k_cat, 0}, b.dA_c1, h, w));
+        GRC(dgrad(c.c1, b.dA_c1, h, w, b.dcat, h, w, 0));
 
         GRC(bn_bwd(c.bcat, b.dcat, b.cat, b.k_cat, 0, h, w, b.m_cat));
-        DySrc s_cat{b.dcat, b.cat, b.k_cat, b.m_cat, DY_BN};
         const int C = 4 + c.cdeep, hu = b.hd, wu = b.wd;
         const int oyu = (2 * hu - h) / 2, oxu = (2 * wu - w) / 2;
         {
             dim3 grid(min(ceil_div(4 * h * w, 256), 148 * 8), 1, N);
-            cat_bwd_skip_kernel<<<grid, 256, 0, st>>>(s_cat, C, h, w, 4, h, w, 0, 0, b.dA_s);
+            cat_bwd_skip_kernel<<<grid, 256, 0, st>>>(b.dcat, C, h, w, 4, h, w, 0, 0, b.dA_s);
             SPLICE_LAUNCH_CHECK();
             float* dU = (i == GEN_SCALES - 1) ? b.dA_d2 : s.sb[i + 1].dA_c2;
             dim3 grid2(min(ceil_div(c.cdeep * hu * wu, 256), 148 * 8), 1, N);
-            cat_bwd_up_kernel<<<grid2, 256, 0, st>>>(s_cat, C, h, w, 4, c.cdeep, hu, wu, oyu, oxu, dU);
+            cat_bwd_up_kernel<<<grid2, 256, 0, st>>>(b.dcat, C, h, w, 4, c.cdeep, hu, wu, oyu, oxu, dU);
             SPLICE_LAUNCH_CHECK();
         }
     }
@@ -801,19 +985,16 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
         float* dIn = (i == 0) ? nullptr : s.sb[i - 1].dA_d2;
 
         GRC(bn_bwd(c.bs, b.dA_s, b.s_raw, b.k_s, 1, b.h, b.w, b.m_s));
-        DySrc s_s{b.dA_s, b.s_raw, b.k_s, b.m_s, DY_BN_LRELU};
-        GRC(wgrad(c.s, in, b.h, b.w, tf_in, s_s, b.h, b.w));
-        if (dIn) GRC(launch_conv_dgrad(1, 1, s_s, N, 4, b.h, b.w, p.param[c.s.pw], c.s.cin, dIn, b.h, b.w, 0, st));
+        GRC(wgrad(c.s, in, b.h, b.w, tf_in, b.dA_s, b.h, b.w));
+        if (dIn) GRC(dgrad(c.s, b.dA_s, b.h, b.w, dIn, b.h, b.w, 0));
 
         GRC(bn_bwd(c.bd2, b.dA_d2, b.d2_raw, b.k_d2, 1, b.hd, b.wd, b.m_d2));
-        DySrc s_d2{b.dA_d2, b.d2_raw, b.k_d2, b.m_d2, DY_BN_LRELU};
-        GRC(wgrad(c.d2, b.d1_raw, b.hd, b.wd, InTf{b.k_d1, 1}, s_d2, b.hd, b.wd));
-        GRC(launch_conv_dgrad(3, 1, s_d2, N, c.d2.cout, b.hd, b.wd, p.param[c.d2.pw], c.d2.cin, b.dA_d1, b.hd, b.wd, 0, st));
+        GRC(wgrad(c.d2, b.d1_raw, b.hd, b.wd, InTf{b.k_d1, 1}, b.dA_d2, b.hd, b.wd));
+        GRC(dgrad(c.d2, b.dA_d2, b.hd, b.wd, b.dA_d1, b.hd, b.wd, 0));
 
         GRC(bn_bwd(c.bd1, b.dA_d1, b.d1_raw, b.k_d1, 1, b.hd, b.wd, b.m_d1));
-        DySrc s_d1{b.dA_d1, b.d1_raw, b.k_d1, b.m_d1, DY_BN_LRELU};
-        GRC(wgrad(c.d1, in, b.h, b.w, tf_in, s_d1, b.hd, b.wd));
-        if (dIn) GRC(launch_conv_dgrad(3, 2, s_d1, N, c.d1.cout, b.hd, b.wd, p.param[c.d1.pw], c.d1.cin, dIn, b.h, b.w, 1, st));
+        GRC(wgrad(c.d1, in, b.h, b.w, tf_in, b.dA_d1, b.hd, b.wd));
+        if (dIn) GRC(dgrad(c.d1, b.dA_d1, b.hd, b.wd, dIn, b.h, b.w, 1));
     }
     s.valid = false;
     return SPLICE_OK;

@@ -52,6 +52,8 @@ private:
         const float* x = nullptr;
         float* x_copy = nullptr;
         float* out = nullptr;
+        float* dfin = nullptr;
+        size_t stats_floats = 0;
         ScaleBuf sb[GEN_SCALES];
     };
     int configure(Slot& s, int N, int H, int W);
