@@ -632,15 +632,15 @@ static constexpr int TARGET_BLOCKS = 296;          // two CTAs per SM on 148 SMs
 static constexpr size_t SPLIT_FLOATS = 8u << 20;   // scratch for split partial sums (floats)
 static constexpr size_t WGRAD_FLOATS = 8u << 20;   // scratch for weight-gradient partials (floats)
 
-// channel tile (4 / 8 / 16) and split factor that bring a layer's grid to >= TARGET_BLOCKS where possible
+// Channel tile and split factor of a layer. A thread does CT FMAs per loaded tap, so wide channel tiles are kept
+// (CT = 16 whenever the layer has >= 16 fast channels) and grids that would not fill 148 SMs are widened by splitting
+// the reduction channels instead (partials are folded by conv_finish_bn_kernel / sum_partials_kernel).
 static void pick_tiling(int P, int Cfast, int Cslow, size_t out_elems, int* ct, int* split) {
     const int pb = ceil_div(P, CONV_THREADS);
-    int t = Cfast <= 4 ? 4 : 16;
-    if (t == 16 && pb * ceil_div(Cfast, 16) < TARGET_BLOCKS && Cfast >= 8) t = 8;
-    if (t == 8 && pb * ceil_div(Cfast, 8) < TARGET_BLOCKS) t = 4;
+    const int t = Cfast <= 4 ? 4 : (Cfast <= 8 ? 8 : 16);
     int sk = 1;
     const int blocks = pb * ceil_div(Cfast, t);
-    if (blocks < TARGET_BLOCKS) {
+    if (blocks < TARGET_BLOCKS && P <= 16384) {
         sk = ceil_div(TARGET_BLOCKS, blocks);
         const int max_sk = Cslow / 8 > 0 ? Cslow / 8 : 1;          // at least 8 reduction channels per split
         if (sk > max_sk) sk = max_sk;

@@ -120,3 +120,16 @@ def test_lambda_schedule_matches_oracle():
         crit.update_lambda_config(torch.tensor([float(step)]))
         state = R.active_lambdas(cfg, step, state)
         assert {k: float(v) for k, v in crit.lambdas.items()} == {k: float(v) for k, v in state.items()}, step
+
+
+def test_install_as_reference_modules_aliases_every_mirror():
+    import subprocess, sys
+    from pathlib import Path
+
+    code = ("import splice_b200, sys; splice_b200.install_as_reference_modules();"
+            "import models.model, util.losses, util.util, data.Dataset, models.unet.skip, models.extractor;"
+            "assert models.model.Model.__module__ == 'splice_b200.models.model';"
+            "assert util.losses.LossG.__module__ == 'splice_b200.util.losses';"
+            "from models.extractor import VitExtractor, attn_cosine_sim; print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(Path(__file__).resolve().parents[1]))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
