@@ -82,15 +82,31 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
     const int cps = (Cin + splitK - 1) / splitK;
     const int c_begin = blockIdx.z * cps, c_end = min(Cin, c_begin + cps);
     const int iy0 = oy * S - PAD, ix0 = ox * S - PAD;
+    // taps are loaded unconditionally from clamped coordinates (so the 9 loads of a channel issue back to back and the
+    // next channel's taps are prefetched while this one's FMAs run); out-of-image taps are zeroed by mask afterwards
+    int yoff[K], xoff[K];
     bool rok[K], cok[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         rok[k] = active && iy0 + k >= 0 && iy0 + k < Hin;
         cok[k] = ix0 + k >= 0 && ix0 + k < Win;
+        yoff[k] = min(max(iy0 + k, 0), Hin - 1) * Win;
+        xoff[k] = min(max(ix0 + k, 0), Win - 1);
     }
     float acc[CO_T];
 #pragma unroll
     for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+    const size_t plane = (size_t)Hin * Win;
+    const float* xn = x + (size_t)n * Cin * plane;
+    float cur[KK], nxt[KK];
+    auto load_taps = [&](float (&v)[KK], int c) {
+        const float* base = xn + (size_t)c * plane;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) v[ky * K + kx] = __ldg(base + yoff[ky] + xoff[kx]);
+    };
+    if (c_begin < c_end) load_taps(nxt, c_begin);
 
     for (int c0 = c_begin; c0 < c_end; c0 += CI_C) {
         const int cn = min(CI_C, c_end - c0);
@@ -105,20 +121,20 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
         }
         __syncthreads();
         for (int ci = 0; ci < cn; ++ci) {
-            const float* base = x + ((size_t)(n * Cin + c0 + ci) * Hin) * Win;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) cur[kk] = nxt[kk];
+            if (c0 + ci + 1 < c_end) load_taps(nxt, c0 + ci + 1);
             const float2 ab = s_ab[ci];
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    float v = 0.f;
-                    if (rok[ky] && cok[kx]) {
-                        v = __ldg(base + (size_t)(iy0 + ky) * Win + ix0 + kx);
-                        if (tf.k) {
-                            v = fmaf(ab.x, v, ab.y);
-                            if (tf.lrelu && v < 0.f) v *= LRELU;
-                        }
-                    }   // zero padding lives in the post-BN/activation domain, like the reference
+                    float v = cur[ky * K + kx];
+                    if (tf.k) {
+                        v = fmaf(ab.x, v, ab.y);
+                        if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
+                    }
+                    v = (rok[ky] && cok[kx]) ? v : 0.f;   // zero padding lives in the post-BN/activation domain
 #pragma unroll
                     for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v, s_w[ci][ky * K + kx][co], acc[co]);
                 }
@@ -422,16 +438,31 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* _
     const int ci0 = blockIdx.y * CI_T;
     const int cps = (Cout + splitK - 1) / splitK;
     const int c_begin = blockIdx.z * cps, c_end = min(Cout, c_begin + cps);
-    int oyk[K], oxk[K];   // output row / column reached through tap k, or -1
+    // taps: output row / column reached through tap k (clamped so that loads are unconditional) + validity
+    int yoff[K], xoff[K];
+    bool rok[K], cok[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int ty = iy + PAD - k, tx = ix + PAD - k;
-        oyk[k] = (active && ty >= 0 && ty % S == 0 && ty / S < Ho) ? ty / S : -1;
-        oxk[k] = (tx >= 0 && tx % S == 0 && tx / S < Wo) ? tx / S : -1;
+        rok[k] = active && ty >= 0 && ty % S == 0 && ty / S < Ho;
+        cok[k] = tx >= 0 && tx % S == 0 && tx / S < Wo;
+        yoff[k] = (rok[k] ? ty / S : 0) * Wo;
+        xoff[k] = cok[k] ? tx / S : 0;
     }
     float acc[CI_T];
 #pragma unroll
     for (int i = 0; i < CI_T; ++i) acc[i] = 0.f;
+    const size_t plane = (size_t)Ho * Wo;
+    const float* dyn = dy + (size_t)n * Cout * plane;
+    float cur[KK], nxt[KK];
+    auto load_taps = [&](float (&v)[KK], int c) {
+        const float* base = dyn + (size_t)c * plane;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) v[ky * K + kx] = __ldg(base + yoff[ky] + xoff[kx]);
+    };
+    if (c_begin < c_end) load_taps(nxt, c_begin);
     for (int c0 = c_begin; c0 < c_end; c0 += CO_C) {
         const int cn = min(CO_C, c_end - c0);
         for (int idx = threadIdx.x; idx < CO_C * KK * CI_T; idx += CONV_THREADS) {
@@ -440,13 +471,14 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* _
         }
         __syncthreads();
         for (int co = 0; co < cn; ++co) {
-            const float* base = dy + ((size_t)(n * Cout + c0 + co) * Ho) * Wo;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) cur[kk] = nxt[kk];
+            if (c0 + co + 1 < c_end) load_taps(nxt, c0 + co + 1);
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    float v = 0.f;
-                    if (oyk[ky] >= 0 && oxk[kx] >= 0) v = __ldg(base + (size_t)oyk[ky] * Wo + oxk[kx]);
+                    const float v = (rok[ky] && cok[kx]) ? cur[ky * K + kx] : 0.f;
 #pragma unroll
                     for (int ci = 0; ci < CI_T; ++ci) acc[ci] = fmaf(v, s_w[co][ky * K + kx][ci], acc[ci]);
                 }
