@@ -56,7 +56,7 @@ typedef struct SpliceGemmArgs {
     int rows_per_seq;                /* 0 = no token remap */
     const void* pos; int ldpos;      /* fp32 pos_embed [1+rows_per_seq, ldpos] */
     void* slice32; int slice_c0, slice_c1, ldslice;
-    int impl;                        /* 0 = tcgen05 (product path), 1 = SIMT cross-check (tests only) */
+    int impl;                        /* 0 = tcgen05 persistent (product path), 1 = SIMT cross-check (tests only), 2 = tcgen05 one-tile-per-CTA */
     int bn_hint;                     /* 0 = auto; 64 / 128 / 256 */
 } SpliceGemmArgs;
 SPLICE_API int splice_gemm_bf16(const SpliceGemmArgs* args, void* stream);

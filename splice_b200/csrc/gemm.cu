@@ -137,6 +137,142 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant (product path): one CTA per SM loops over output tiles (n fastest, so co-scheduled CTAs share
+// the A row block through L2). The accumulator is double-buffered in TMEM (2 x BN columns): while the 8 epilogue
+// warps drain tile i (TMEM -> registers -> fused epilogue -> global), the MMA warp already accumulates tile i+1.
+//   warp 0      TMA producer        warp 1   MMA issuer (+ TMEM alloc/dealloc)       warps 2..9   epilogue
+// Epilogue warp e reads TMEM lane quadrant (warp_id % 4) and the column half (e / 4) of the tile.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(320, 1)
+gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
+                                    int N, int K, GemmEpilogue ep) {
+    using L = GemmSmem<BN, STAGES>;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static_assert(2 * BN <= 512, "two accumulator stages must fit the 512 TMEM columns");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + STAGES * L::A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILES_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = K / BK;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int num_tiles = tiles_n * ((M + BM - 1) / BM);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar[0], 1);
+        mbar_init(&tmem_full_bar[1], 1);
+        mbar_init(&tmem_empty_bar[0], 8);   // one arrival per epilogue warp
+        mbar_init(&tmem_empty_bar[1], 8);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;   // running k-block counter across tiles (ring position)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                    tma_load_2d(smemA + s * L::A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(smemB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            uint32_t it = 0, lt = 0;   // k-block counter, local tile counter
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t as = lt & 1u;
+                mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + s * L::A_BYTES));
+                    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + s * L::B_BYTES));
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)
+                        umma_bf16_ss(tacc, adesc + 2u * j, bdesc + 2u * j, idesc, (kb | j) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        const int e = warp - 2;            // 0..7
+        const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+        const int half = e >> 2;           // column half of the tile
+        constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const uint32_t as = lt & 1u;
+            const int row = m0 + quad * 32 + lane;
+            mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < CH_PER_HALF; ++cc) {
+                const int c = half * CH_PER_HALF + cc;
+                const int col = n0 + c * 32;
+                if (c < CHUNKS && col < N) {  // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+                    tmem_ld_wait();
+                    if (row < M) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        gemm_epilogue_chunk(ep, row, col, v);
+                    }
+                }
+            }
+            // all of this warp's TMEM reads of stage `as` are complete: hand the stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SIMT cross-check kernel (same operands, same epilogue). Not on the product path: selected only by
 // impl == GEMM_IMPL_SIMT from the unit tests to separate "tcgen05 plumbing" from "epilogue logic".
 // ------------------------------------------------------------------------------------------------
@@ -232,6 +368,28 @@ static int launch_tcgen05(const bf16* A, int lda, const bf16* B, int ldb, int M,
     return SPLICE_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep,
+                             cudaStream_t stream) {
+    using L = GemmSmem<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPLICE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<BN, STAGES>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+    if (rc) return rc;
+    const int tiles = ceil_div(N, BN) * ceil_div(M, BM);
+    const int grid = tiles < 148 ? tiles : 148;
+    gemm_bf16_tcgen05_persistent_kernel<BN, STAGES><<<grid, 320, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep);
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep, int impl,
                  int bn_hint, cudaStream_t stream) {
     SPLICE_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -259,28 +417,38 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     }
+    if (impl == GEMM_IMPL_TCGEN05_TILE) {   // first-generation one-tile-per-CTA kernel (kept for A/B comparison)
+        switch (bn_hint) {
+            case 64:  return launch_tcgen05<64, 4>(A, lda, B, ldb, M, N, K, ep, stream);
+            case 256: return launch_tcgen05<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
+            default:  return launch_tcgen05<128, 3>(A, lda, B, ldb, M, N, K, ep, stream);
+        }
+    }
     SPLICE_REQUIRE(impl == GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
 
     int bn = bn_hint;
     if (bn == 0) {
-        // Per-SM work model: the busiest SM executes ceil(tiles / 148) tiles of width c. Narrow tiles are
-        // penalised because a 128 x c MMA re-reads the 128-row A tile from shared memory for fewer FLOPs
-        // (128x64 needs 192 B/clk of smem operand bandwidth, above the 128 B/clk an SM has).
+        // Persistent-kernel cost model: the busiest SM runs ceil(tiles / 148) tiles; a tile costs ~BN (epilogue and
+        // MMA both scale with BN) plus a fixed per-tile overhead; narrow tiles re-read the A row block N/BN times
+        // through L2 (bytes term, ~8 TB/s of L2->SM bandwidth expressed in the same units).
         const int mt = ceil_div(M, BM);
         const int cand[3] = {256, 128, 64};
-        const double penalty[3] = {1.0, 1.1, 1.4};
         double best = 1e30;
         for (int i = 0; i < 3; ++i) {
             const int c = cand[i];
             const long tiles = (long)mt * ceil_div(N, c);
-            const double cost = (double)((tiles + 147) / 148) * c * penalty[i];
+            const double rounds = (double)((tiles + 147) / 148);
+            const double t_tiles = rounds * (c + 24.0) * (K / 768.0 < 1.0 ? 1.0 : (0.5 + 0.5 * K / 768.0));
+            const double l2_bytes = ((double)ceil_div(N, c) * M + (double)mt * N) * K * 2.0;
+            const double t_l2 = l2_bytes / 8e12 * 1e6 * 11.0;   // us -> tile units (a 128-wide, K=768 tile ~ 2.2 us)
+            const double cost = t_tiles > t_l2 ? t_tiles : t_l2;
             if (cost < best) { best = cost; bn = c; }
         }
     }
     switch (bn) {
-        case 64:  return launch_tcgen05<64, 4>(A, lda, B, ldb, M, N, K, ep, stream);
-        case 128: return launch_tcgen05<128, 3>(A, lda, B, ldb, M, N, K, ep, stream);
-        case 256: return launch_tcgen05<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
+        case 64:  return launch_persistent<64, 6>(A, lda, B, ldb, M, N, K, ep, stream);
+        case 128: return launch_persistent<128, 5>(A, lda, B, ldb, M, N, K, ep, stream);
+        case 256: return launch_persistent<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
         default: break;
     }
     set_error("gemm: unsupported BN %d", bn);

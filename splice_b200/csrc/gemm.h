@@ -34,7 +34,7 @@ struct GemmEpilogue {
     int slice_c0 = 0, slice_c1 = 0, ldslice = 0;
 };
 
-enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1 };
+enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1, GEMM_IMPL_TCGEN05_TILE = 2 };
 
 // Launches on `stream`. bn_hint: 0 = pick automatically, else one of 64/128/256.
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep,

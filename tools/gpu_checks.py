@@ -152,53 +152,46 @@ def gemm_tc_epilogues():
 
 @check
 def gemm_tc_timing():
-    """TFLOP/s of the ViT-B/8 shapes at M = 4*785 (forward) and 2*785 (backward), CUDA events, L2 flushed."""
+    """TFLOP/s of the ViT-B/8 shapes at M = 4*785 (forward) and 2*785 (backward): 20 back-to-back launches between
+    CUDA events (so host launch cost is hidden), operands L2-warm as they are inside the step."""
     import torch
     from splice_b200 import ops
 
     shapes = [(3140, 2304, 768), (3140, 768, 768), (3140, 3072, 768), (3140, 768, 3072),
-              (1570, 3072, 768), (1570, 768, 3072), (1570, 768, 2304), (3136, 768, 192)]
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+              (1570, 3072, 768), (1570, 768, 3072), (1570, 768, 2304), (1570, 768, 768), (3136, 768, 192)]
     out = []
+    reps = 20
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3   # us
+
     for (M, N, K) in shapes:
         A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
         C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         row = {"M": M, "N": N, "K": K}
+        gf = 2.0 * M * N * K / 1e6   # MFLOP -> TFLOP/s = gf / us
         for bn in (64, 128, 256):
-            for _ in range(3):
-                ops.gemm(A, B, out16=C, bn_hint=bn)
-            ts = []
-            for _ in range(10):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ops.gemm(A, B, out16=C, bn_hint=bn)
-                e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ms = sorted(ts)[len(ts) // 2]
-            row[f"bn{bn}_us"] = ms * 1e3
-            row[f"bn{bn}_tflops"] = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-        # cuBLAS for context
-        for _ in range(3):
-            torch.matmul(A, B.t())
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(A, B.t())
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        row["cublas_us"] = ms * 1e3
-        row["cublas_tflops"] = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+            us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=bn))
+            row[f"persist_bn{bn}"] = round(gf / us, 1)
+        us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=0))
+        row["persist_auto"] = round(gf / us, 1)
+        us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=128, impl=2))
+        row["tile_bn128"] = round(gf / us, 1)
+        us = timeit(lambda: torch.matmul(A, B.t()))
+        row["cublas"] = round(gf / us, 1)
         row["ok"] = True
         out.append(row)
     return out
-
 
 
 # ------------------------------------------------------------------------------------------------
