@@ -428,22 +428,12 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
 
     int bn = bn_hint;
     if (bn == 0) {
-        // Persistent-kernel cost model: the busiest SM runs ceil(tiles / 148) tiles; a tile costs ~BN (epilogue and
-        // MMA both scale with BN) plus a fixed per-tile overhead; narrow tiles re-read the A row block N/BN times
-        // through L2 (bytes term, ~8 TB/s of L2->SM bandwidth expressed in the same units).
-        const int mt = ceil_div(M, BM);
-        const int cand[3] = {256, 128, 64};
-        double best = 1e30;
-        for (int i = 0; i < 3; ++i) {
-            const int c = cand[i];
-            const long tiles = (long)mt * ceil_div(N, c);
-            const double rounds = (double)((tiles + 147) / 148);
-            const double t_tiles = rounds * (c + 24.0) * (K / 768.0 < 1.0 ? 1.0 : (0.5 + 0.5 * K / 768.0));
-            const double l2_bytes = ((double)ceil_div(N, c) * M + (double)mt * N) * K * 2.0;
-            const double t_l2 = l2_bytes / 8e12 * 1e6 * 11.0;   // us -> tile units (a 128-wide, K=768 tile ~ 2.2 us)
-            const double cost = t_tiles > t_l2 ? t_tiles : t_l2;
-            if (cost < best) { best = cost; bn = c; }
-        }
+        // Measured on B200 (tools/gpu_checks.py gemm_tc_timing, ViT-B/8 shapes): the 128x256 tile wins whenever there are
+        // enough tiles to occupy the 148 persistent CTAs (it halves the A re-reads through L2, which bound the 128-wide
+        // tiles); the short-M backward GEMMs with N = 768 prefer 128x128; sub-128 widths only for narrow outputs.
+        if (N % 256 == 0 && (M >= 2048 || N >= 2048)) bn = 256;
+        else if (N >= 128) bn = 128;
+        else bn = 64;
     }
     switch (bn) {
         case 64:  return launch_persistent<64, 6>(A, lda, B, ldb, M, N, K, ep, stream);
