@@ -120,6 +120,7 @@ typedef struct SpliceVitForwardArgs {
     void* block32_all;     /* out fp32 [depth, n_images*t, D]  (compat taps), or NULL */
     int gemm_impl;         /* 0 = tcgen05 */
     int pre_normalized;    /* 1 = images are already ImageNet-normalised (VitExtractor API), skip (x-mean)/std */
+    int use_graph;         /* 1 = the caller reuses the same output buffers every call: capture + replay a CUDA graph */
 } SpliceVitForwardArgs;
 SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* args, void* stream);
 
@@ -131,6 +132,7 @@ typedef struct SpliceVitBackwardArgs {
     const void* dcls32;        /* fp32 [n_grad, D] or NULL */
     const SpliceImage* grads;  /* host array, n_grad entries; data = fp32 [3,h,w] out (NULL entry = skip) */
     int gemm_impl;
+    int use_graph;             /* 1 = dkeys32 / dcls32 are the same buffers every call: CUDA graph replay */
 } SpliceVitBackwardArgs;
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* args, void* stream);
 
@@ -179,6 +181,8 @@ SPLICE_API int splice_gen_destroy(void* ctx);
 /* out[N,3,H,W] = netG(x[N,3,H,W]); keep != 0 retains the activations in `slot` (0..3) for splice_gen_backward */
 SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const void* x, int N, int H, int W, void* out,
                                   int slot, int keep, int update_running, void* stream);
+/* 1 (default) = replay CUDA graphs keyed by (slot, shape, pointer table); 0 = always launch eagerly */
+SPLICE_API int splice_gen_set_graphs(void* ctx, int on);
 /* parameter gradients += d loss / d params given dout[N,3,H,W] = d loss / d out of the forward kept in `slot` */
 SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream);
 

@@ -72,6 +72,7 @@ class SpliceVitForwardArgs(C.Structure):
         ("keys32", c_void_p), ("cls32", c_void_p), ("qkv32_all", c_void_p), ("block32_all", c_void_p),
         ("gemm_impl", c_int),
         ("pre_normalized", c_int),
+        ("use_graph", c_int),
     ]
 
 
@@ -81,6 +82,7 @@ class SpliceVitBackwardArgs(C.Structure):
         ("dkeys32", c_void_p), ("dcls32", c_void_p),
         ("grads", C.POINTER(SpliceImage)),
         ("gemm_impl", c_int),
+        ("use_graph", c_int),
     ]
 
 
@@ -144,6 +146,7 @@ splice_gen_destroy = _sig("splice_gen_destroy", c_int, [c_void_p])
 splice_gen_forward = _sig("splice_gen_forward", c_int,
                           [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                            c_void_p])
+splice_gen_set_graphs = _sig("splice_gen_set_graphs", c_int, [c_void_p, c_int])
 splice_gen_backward = _sig("splice_gen_backward", c_int, [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_void_p])
 splice_adam_step = _sig("splice_adam_step", c_int,
                         [C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
@@ -157,7 +160,7 @@ EXPORTS = [
     "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd", "splice_resize_normalize",
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
-    "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward",
+    "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward", "splice_gen_set_graphs",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
 

@@ -31,6 +31,7 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 
 }  // namespace splice
 
@@ -125,6 +126,7 @@ SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* a, void
     v.n_grad = a->n_grad; v.slot = a->slot; v.keys32 = (float*)a->keys32; v.cls32 = (float*)a->cls32;
     v.qkv32_all = (float*)a->qkv32_all; v.block32_all = (float*)a->block32_all; v.gemm_impl = a->gemm_impl;
     v.pre_normalized = a->pre_normalized != 0;
+    v.use_graph = a->use_graph != 0;
     return static_cast<VitEngine*>(ctx)->forward(v, (cudaStream_t)stream);
 }
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, void* stream) {
@@ -137,6 +139,7 @@ SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, vo
     for (int i = 0; i < n; ++i) g[i] = ImageGradRef{(float*)a->grads[i].data, a->grads[i].h, a->grads[i].w};
     VitBackwardArgs v;
     v.slot = a->slot; v.dkeys32 = (const float*)a->dkeys32; v.dcls32 = (const float*)a->dcls32; v.gemm_impl = a->gemm_impl;
+    v.use_graph = a->use_graph != 0;
     v.grads = g;
     return e->backward(v, (cudaStream_t)stream);
 }
@@ -278,6 +281,11 @@ SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const v
             SPLICE_REQUIRE(g.running_mean[i] && g.running_var[i] && g.num_batches_tracked[i], "splice_gen_forward: BN buffer %d is null", i);
     return static_cast<GenEngine*>(ctx)->forward(g, (const float*)x, N, H, W, (float*)out, slot, keep != 0, update_running != 0,
                                                  (cudaStream_t)stream);
+}
+SPLICE_API int splice_gen_set_graphs(void* ctx, int on) {
+    SPLICE_REQUIRE(ctx, "splice_gen_set_graphs: null ctx");
+    static_cast<GenEngine*>(ctx)->set_graphs(on != 0);
+    return SPLICE_OK;
 }
 SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream) {
     SPLICE_REQUIRE(ctx && p, "splice_gen_backward: null argument");

@@ -14,6 +14,9 @@
 #include <cudaTypedefs.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "gemm.h"
 
 namespace splice {
@@ -325,8 +328,38 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
     return fn;
 }
 
+// Encoded tensor maps are cached: the engine's operands live at stable addresses (weights, per-slot workspaces), so
+// after the first step every GEMM launch finds its two descriptors here instead of paying two driver calls.
+struct TmapKey {
+    const void* ptr; int rows, cols, ld, box_rows;
+    bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + ((size_t)k.cols << 20) + ((size_t)k.ld << 40) + (size_t)k.box_rows;
+        return h;
+    }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+
+static int make_tmap_bf16_uncached(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows);
+
 // 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64, 128B swizzle.
 static int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows) {
+    const TmapKey key{ptr, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *tm = it->second; return SPLICE_OK; }
+    int rc = make_tmap_bf16_uncached(tm, ptr, rows, cols, ld, box_rows);
+    if (rc) return rc;
+    if (g_tmaps.size() > 4096) g_tmaps.clear();   // unbounded growth guard (pointer churn from ad-hoc callers)
+    g_tmaps.emplace(key, *tm);
+    return SPLICE_OK;
+}
+
+static int make_tmap_bf16_uncached(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = get_tmap_encoder();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old or no GPU)");

@@ -811,6 +811,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     plan((size_t)N * 3 * H * W * 4);  // x copy
     plan((size_t)N * 3 * H * W * 4);  // out copy
     plan((size_t)N * 3 * H * W * 4);  // d(pre-sigmoid)
+    plan((size_t)N * 3 * H * W * 4);  // dout copy (stable address for the backward graph)
     if (off > s.pool_bytes) {
         SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
         cudaFree(s.pool);
@@ -833,6 +834,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     s.x_copy = (float*)nx();
     s.out = (float*)nx();
     s.dfin = (float*)nx();
+    s.dout_copy = (float*)nx();
     s.N = N; s.H = H; s.W = W;
     s.valid = false;
     return SPLICE_OK;
@@ -854,6 +856,29 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
     const size_t stats_floats = (size_t)ceil_div(N * H * W, CONV_THREADS) * 132 * 3 + (size_t)N * ceil_div(H, TH) * ceil_div(W, TW) * 132 * 3;
     GRC(ensure_scratch((stats_floats + SPLIT_FLOATS + WGRAD_FLOATS) * sizeof(float) + 4096));
     s.stats_floats = stats_floats;
+    // keep a private copy of the input: the caller's tensor may be freed before backward() (wgrad of scale 0 reads it)
+    SPLICE_CHECK_CUDA(cudaMemcpyAsync(s.x_copy, x, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s.x = s.x_copy;
+
+    if (use_graphs_) {
+        KeyHasher k;
+        k.add((uint64_t)11).add((uint64_t)slot).add((uint64_t)N).add((uint64_t)H).add((uint64_t)W).add((uint64_t)update_running)
+            .add(s.pool).add(scratch_);
+        for (int i = 0; i < GEN_PARAMS; ++i) k.add(p.param[i]);
+        if (update_running)
+            for (int i = 0; i < GEN_BN; ++i) k.add(p.running_mean[i]).add(p.running_var[i]).add(p.num_batches_tracked[i]);
+        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return forward_body(p, s, update_running, cs); }));
+    } else {
+        GRC(forward_body(p, s, update_running, st));
+    }
+    SPLICE_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s.valid = keep;
+    return SPLICE_OK;
+}
+
+int GenEngine::forward_body(const GenPointers& p, Slot& s, bool update_running, cudaStream_t st) {
+    const int N = s.N, H = s.H, W = s.W;
+    const size_t stats_floats = s.stats_floats;
     float* part = static_cast<float*>(scratch_);
     float* split = part + stats_floats;
     const float eps = 1e-5f, mom = 0.1f;
@@ -868,10 +893,6 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
         return launch_conv_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, p.param[c.pw], p.param[c.pb], c.cout, y, ho, wo, 0, &bo, part,
                                split, st);
     };
-
-    // keep a private copy of the input: the caller's tensor may be freed before backward() (wgrad of scale 0 reads it)
-    SPLICE_CHECK_CUDA(cudaMemcpyAsync(s.x_copy, x, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    s.x = s.x_copy;
 
     // down path
     const float* in = s.x;
@@ -910,8 +931,6 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
     }
     GRC(launch_conv_fwd(1, 1, s.sb[0].c2_raw, N, final_.cin, H, W, InTf{s.sb[0].k_c2, 1}, p.param[final_.pw], p.param[final_.pb], 3,
                         s.out, H, W, 1, nullptr, nullptr, nullptr, st));
-    SPLICE_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    s.valid = keep;
     return SPLICE_OK;
 }
 
@@ -920,6 +939,20 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
     Slot& s = slots_[slot];
     SPLICE_REQUIRE(s.pool && s.valid, "generator backward: slot %d holds no kept forward pass", slot);
     SPLICE_REQUIRE(dout, "generator backward: null gradient");
+    SPLICE_CHECK_CUDA(cudaMemcpyAsync(s.dout_copy, dout, (size_t)s.N * 3 * s.H * s.W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (use_graphs_) {
+        KeyHasher k;
+        k.add((uint64_t)12).add((uint64_t)slot).add((uint64_t)s.N).add((uint64_t)s.H).add((uint64_t)s.W).add(s.pool).add(scratch_);
+        for (int i = 0; i < GEN_PARAMS; ++i) k.add(p.param[i]).add(p.grad[i]);
+        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return backward_body(p, s, cs); }));
+    } else {
+        GRC(backward_body(p, s, st));
+    }
+    s.valid = false;
+    return SPLICE_OK;
+}
+
+int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
     const int N = s.N, H = s.H, W = s.W;
     float* part = static_cast<float*>(scratch_);
     float* split = part + s.stats_floats;
@@ -977,7 +1010,7 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
     // final 1x1 conv + sigmoid
     {
         const size_t total = (size_t)N * 3 * H * W;
-        sigmoid_bwd_kernel<<<(int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, st>>>(dout, s.out, s.dfin, total);
+        sigmoid_bwd_kernel<<<(int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, st>>>(s.dout_copy, s.out, s.dfin, total);
         SPLICE_LAUNCH_CHECK();
         GRC(wgrad(final_, s.sb[0].c2_raw, H, W, InTf{s.sb[0].k_c2, 1}, s.dfin, H, W));
         GRC(dgrad(final_, s.dfin, H, W, s.sb[0].dA_c2, H, W, 0));
@@ -1028,7 +1061,6 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
         GRC(wgrad(c.d1, in, b.h, b.w, tf_in, b.dA_d1, b.hd, b.wd));
         if (dIn) GRC(dgrad(c.d1, b.dA_d1, b.hd, b.wd, dIn, b.h, b.w, 1));
     }
-    s.valid = false;
     return SPLICE_OK;
 }
 

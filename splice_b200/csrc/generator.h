@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "graph.h"
 
 namespace splice {
 
@@ -28,6 +29,7 @@ public:
                 bool update_running, cudaStream_t stream);
     // dout [N,3,H,W] -> parameter gradients accumulated into p.grad; dx (optional) = d loss / d input
     int backward(const GenPointers& p, const float* dout, int slot, cudaStream_t stream);
+    void set_graphs(bool on) { use_graphs_ = on; }
 
 private:
     struct Conv { int cin, cout, k, stride, pw, pb; };         // pw/pb: parameter indices of weight / bias
@@ -53,6 +55,7 @@ private:
         float* x_copy = nullptr;
         float* out = nullptr;
         float* dfin = nullptr;
+        float* dout_copy = nullptr;
         size_t stats_floats = 0;
         ScaleBuf sb[GEN_SCALES];
     };
@@ -62,6 +65,10 @@ private:
     Scale sc_[GEN_SCALES];
     Conv final_;
     Slot slots_[GEN_SLOTS];
+    int forward_body(const GenPointers& p, Slot& s, bool update_running, cudaStream_t st);
+    int backward_body(const GenPointers& p, Slot& s, cudaStream_t st);
+    GraphCache graphs_;
+    bool use_graphs_ = true;
     void* scratch_ = nullptr;      // partial-reduction scratch shared by all calls (stream-ordered reuse)
     size_t scratch_bytes_ = 0;
 };

@@ -273,6 +273,18 @@ int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
     for (int i = 0; i < S; ++i)
         RC(preprocess_fwd(a.images[i].data, a.images[i].h, a.images[i].w, a.out_h, a.out_w, p, s.patches, i * (t - 1),
                           !a.pre_normalized, stream));
+    if (prof_on_ || !a.use_graph) return forward_body(a, s, S, t, pos, stream);
+    KeyHasher k;
+    k.add((uint64_t)1).add((uint64_t)a.slot).add((uint64_t)S).add((uint64_t)t).add((uint64_t)a.n_grad).add(s.pool).add(pos)
+        .add(a.keys32).add(a.cls32).add(a.qkv32_all).add(a.block32_all).add((uint64_t)a.gemm_impl);
+    return graphs_.run(k.h, stream, [&](cudaStream_t st) { return forward_body(a, s, S, t, pos, st); });
+}
+
+// everything of the forward pass that depends only on (slot, S, t, output pointers): graph-captured
+int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, const float* pos, cudaStream_t stream) {
+    const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
+    const int M = S * t;
+    (void)p;
     RC(write_cls_rows(s.x0[0], cls_, pos, S, t, D, stream));
     {
         GemmEpilogue ep;
@@ -326,6 +338,30 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
     const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
     const int t = s.t, Sg = s.n_grad, Mg = Sg * t;
 
+    if (prof_on_ || !a.use_graph) {
+        RC(backward_body(a, s, stream));
+    } else {
+        KeyHasher k;
+        k.add((uint64_t)2).add((uint64_t)a.slot).add((uint64_t)Sg).add((uint64_t)t).add(s.pool).add(a.dkeys32).add(a.dcls32)
+            .add((uint64_t)a.gemm_impl);
+        RC(graphs_.run(k.h, stream, [&](cudaStream_t st) { return backward_body(a, s, st); }));
+    }
+    for (int i = 0; i < Sg; ++i) {
+        SPLICE_REQUIRE(a.grads[i].h == s.imgs[i].h && a.grads[i].w == s.imgs[i].w,
+                       "vit_backward: gradient %d is %dx%d but the forward image was %dx%d", i, a.grads[i].h, a.grads[i].w,
+                       s.imgs[i].h, s.imgs[i].w);
+        if (!a.grads[i].data) continue;
+        RC(preprocess_bwd(s.dpatch, pp3, i * t + 1, s.imgs[i].h, s.imgs[i].w, s.oh, s.ow, p, a.grads[i].data,
+                          !s.pre_normalized, stream));
+    }
+    return SPLICE_OK;
+}
+
+
+int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t stream) {
+    const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
+    const int t = s.t, Sg = s.n_grad, Mg = Sg * t;
+    (void)p;
     SPLICE_CHECK_CUDA(cudaMemsetAsync(s.g, 0, (size_t)Mg * D * sizeof(float), stream));
     SPLICE_CHECK_CUDA(cudaMemsetAsync(s.g16, 0, (size_t)Mg * D * sizeof(bf16), stream));
     bool have_g = false;
@@ -373,14 +409,6 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
         GemmEpilogue ep;
         ep.c32 = s.dpatch; ep.ldc32 = pp3;
         PROF(PROF_GEMM, GEMM_FLOPS(Mg, pp3, D), 0.0, gemm_bf16_tn(s.g16, D, pe_wT_, D, Mg, pp3, D, ep, a.gemm_impl, 0, stream));
-    }
-    for (int i = 0; i < Sg; ++i) {
-        SPLICE_REQUIRE(a.grads[i].h == s.imgs[i].h && a.grads[i].w == s.imgs[i].w,
-                       "vit_backward: gradient %d is %dx%d but the forward image was %dx%d", i, a.grads[i].h, a.grads[i].w,
-                       s.imgs[i].h, s.imgs[i].w);
-        if (!a.grads[i].data) continue;
-        RC(preprocess_bwd(s.dpatch, pp3, i * t + 1, s.imgs[i].h, s.imgs[i].w, s.oh, s.ow, p, a.grads[i].data,
-                          !s.pre_normalized, stream));
     }
     return SPLICE_OK;
 }

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "graph.h"
 
 namespace splice {
 
@@ -27,6 +28,7 @@ struct VitForwardArgs {
     float* block32_all = nullptr;     // [depth, n_images*t, D]    (compat taps)
     int gemm_impl = 0;                // 0 = tcgen05, 1 = SIMT cross-check
     bool pre_normalized = false;
+    bool use_graph = false;
 };
 
 struct VitBackwardArgs {
@@ -35,6 +37,7 @@ struct VitBackwardArgs {
     const float* dcls32 = nullptr;    // [n_grad, D]
     const ImageGradRef* grads = nullptr;  // n_grad entries
     int gemm_impl = 0;
+    bool use_graph = false;
 };
 
 enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN_FWD = 1, PROF_ATTN_BWD = 2, PROF_ROWWISE = 3, PROF_PREPROC = 4, PROF_NCAT = 5 };
@@ -94,6 +97,9 @@ private:
     std::vector<ProfRec> prof_pending_;
     std::vector<cudaEvent_t> prof_pool_;
     ProfTotals prof_tot_[PROF_NCAT] = {};
+    GraphCache graphs_;
+    int forward_body(const VitForwardArgs& a, Slot& s, int S, int t, const float* pos, cudaStream_t stream);
+    int backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t stream);
 };
 
 }  // namespace splice

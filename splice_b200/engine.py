@@ -91,6 +91,8 @@ class VitEngine:
                                      cur_stream()), "splice_vit_create")
         self._pos_cache: Dict[Tuple[int, int], torch.Tensor] = {}
         self._slot_meta: Dict[int, dict] = {}
+        self._out_cache: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._grad_cache: Dict[tuple, tuple] = {}
 
     def __del__(self):
         ctx = getattr(self, "_ctx", None)
@@ -123,7 +125,7 @@ class VitEngine:
     # ---- forward / backward ------------------------------------------------------------------------
     def forward(self, images: Sequence[torch.Tensor], out_hw: Tuple[int, int], n_grad: int = 0, slot: int = 0,
                 want_keys: bool = True, want_cls: bool = True, want_all_qkv: bool = False,
-                want_all_blocks: bool = False, pre_normalized: bool = False) -> Dict[str, torch.Tensor]:
+                want_all_blocks: bool = False, pre_normalized: bool = False, use_graph: bool = False) -> Dict[str, torch.Tensor]:
         """images: fp32 CUDA tensors [3,h,w] in [0,1] (sizes may differ); all are resized to out_hw.
         Returns {'keys': [S,t,D], 'cls': [S,D], 'qkv': [12,S,t,3D], 'block': [12,S,t,D]} (only the requested)."""
         S = len(images)
@@ -139,16 +141,21 @@ class VitEngine:
                 im = im.to(torch.float32).contiguous()
             keep.append(im)
             arr[i] = _lib.SpliceImage(im.data_ptr(), im.shape[1], im.shape[2])
-        out: Dict[str, torch.Tensor] = {}
         dev, D = self.device, self.dim
-        if want_keys:
-            out["keys"] = torch.empty(S, t, D, device=dev)
-        if want_cls:
-            out["cls"] = torch.empty(S, D, device=dev)
-        if want_all_qkv:
-            out["qkv"] = torch.empty(DEPTH, S, t, 3 * D, device=dev)
-        if want_all_blocks:
-            out["block"] = torch.empty(DEPTH, S, t, D, device=dev)
+        ckey = (slot, S, t, want_keys, want_cls, want_all_qkv, want_all_blocks)
+        out: Optional[Dict[str, torch.Tensor]] = self._out_cache.get(ckey) if use_graph else None
+        if out is None:
+            out = {}
+            if want_keys:
+                out["keys"] = torch.empty(S, t, D, device=dev)
+            if want_cls:
+                out["cls"] = torch.empty(S, D, device=dev)
+            if want_all_qkv:
+                out["qkv"] = torch.empty(DEPTH, S, t, 3 * D, device=dev)
+            if want_all_blocks:
+                out["block"] = torch.empty(DEPTH, S, t, D, device=dev)
+            if use_graph:   # stable output addresses let the engine replay a captured CUDA graph (results are
+                self._out_cache[ckey] = out   # overwritten by the next call with the same signature)
         pos = self._pos_for(oh, ow)
         a = _lib.SpliceVitForwardArgs()
         a.images, a.n_images, a.out_h, a.out_w = arr, S, oh, ow
@@ -158,6 +165,7 @@ class VitEngine:
         a.qkv32_all, a.block32_all = ptr(out.get("qkv")), ptr(out.get("block"))
         a.gemm_impl = self.gemm_impl
         a.pre_normalized = 1 if pre_normalized else 0
+        a.use_graph = 1 if use_graph else 0
         check(_lib.splice_vit_forward(self._ctx, C.byref(a), cur_stream()), "splice_vit_forward")
         self._slot_meta[slot] = {"shapes": [(im.shape[1], im.shape[2]) for im in keep[:n_grad]], "t": t, "keep": keep}
         return out
@@ -166,7 +174,19 @@ class VitEngine:
         """One already-normalised [3,h,w] image at ViT resolution (the VitExtractor API contract)."""
         return self.forward([img], (img.shape[1], img.shape[2]), n_grad=0, slot=3, pre_normalized=True, **want)
 
-    def backward(self, slot: int, dkeys: Optional[torch.Tensor], dcls: Optional[torch.Tensor]) -> List[torch.Tensor]:
+    def grad_buffers(self, slot: int, n_grad: int, t: int):
+        """Zeroed (dkeys [n_grad,t,D], dcls [n_grad,D]) with stable addresses (graph replay in backward)."""
+        key = (slot, n_grad, t)
+        if key not in self._grad_cache:
+            self._grad_cache[key] = (torch.zeros(n_grad, t, self.dim, device=self.device),
+                                     torch.zeros(n_grad, self.dim, device=self.device))
+        dk, dc = self._grad_cache[key]
+        dk.zero_()
+        dc.zero_()
+        return dk, dc
+
+    def backward(self, slot: int, dkeys: Optional[torch.Tensor], dcls: Optional[torch.Tensor],
+                 use_graph: bool = False) -> List[torch.Tensor]:
         """d(loss)/d(image) for the first n_grad images of the forward held in `slot`."""
         meta = self._slot_meta[slot]
         n = len(meta["shapes"])
@@ -181,6 +201,7 @@ class VitEngine:
         if dcls is not None:
             assert dcls.dtype == torch.float32 and dcls.is_contiguous() and dcls.numel() == n * self.dim
         a.dkeys32, a.dcls32, a.grads, a.gemm_impl = ptr(dkeys), ptr(dcls), arr, self.gemm_impl
+        a.use_graph = 1 if use_graph else 0
         check(_lib.splice_vit_backward(self._ctx, C.byref(a), cur_stream()), "splice_vit_backward")
         return grads
 

@@ -153,10 +153,9 @@ class LossG(torch.nn.Module):
         for slot, (hw, members) in enumerate(groups.items()):
             members.sort(key=lambda s: not s["gen"])
             n_grad = sum(1 for s in members if s["gen"])
-            feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot)
+            feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot, use_graph=True)
             t = feats["keys"].shape[1]
-            dkeys = torch.zeros(n_grad, t, eng.dim, device=device) if n_grad else None
-            dcls = torch.zeros(n_grad, eng.dim, device=device) if n_grad else None
+            dkeys, dcls = eng.grad_buffers(slot, n_grad, t) if n_grad else (None, None)
             for j, s in enumerate(members):
                 s.update(keys=feats["keys"][j], cls=feats["cls"][j], slot=slot, idx=j,
                          dkeys=dkeys[j] if s["gen"] else None, dcls=dcls[j] if s["gen"] else None)
@@ -189,7 +188,7 @@ class LossG(torch.nn.Module):
             grp = members[0]["group"]
             if grp["n_grad"] == 0:
                 continue
-            img_grads = eng.backward(grp["slot"], grp["dkeys"], grp["dcls"])
+            img_grads = eng.backward(grp["slot"], grp["dkeys"], grp["dcls"], use_graph=True)
             for s, gimg in zip(members[:grp["n_grad"]], img_grads):
                 b = s["batch"]
                 if id(b) not in grads_by_batch:
