@@ -127,8 +127,14 @@ class NativeSkip(nn.Sequential):
         n, _, h, w = x.shape
         out = torch.empty_like(x)
         if keep:
-            slot = self._next_slot
-            self._next_slot = (self._next_slot + 1) % _KEEP_SLOTS
+            # lowest free slot: the same call site gets the same slot every step (x_global -> 0, y_global -> 1, ...),
+            # which keeps the engine's (slot, shape) CUDA-graph keys few; a never-backwarded pass is recycled last
+            free = [i for i in range(_KEEP_SLOTS) if self._slot_tokens[i] is None]
+            if free:
+                slot = free[0]
+            else:
+                slot = self._next_slot
+                self._next_slot = (self._next_slot + 1) % _KEEP_SLOTS
         else:
             slot = 3
         self._token += 1
