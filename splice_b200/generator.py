@@ -19,6 +19,17 @@ from ._lib import check, cur_stream
 _KEEP_SLOTS = 3      # x_global, y_global, x_entire may be alive at once; slot 3 serves no-grad calls
 
 
+def pick_keep_slot(tokens) -> int:
+    """Activation slot for a netG call whose backward is still to come. Lowest free slot first: the same call site
+    gets the same slot every step (x_global -> 0, y_global -> 1, ...), which keeps the engine's (slot, shape)
+    CUDA-graph keys few. When all are held, recycle the OLDEST pass: the one whose backward never came (step 0's
+    y_global feeds no active loss term, util/losses.py:35-37), never a pass of the current step."""
+    free = [i for i in range(_KEEP_SLOTS) if tokens[i] is None]
+    if free:
+        return free[0]
+    return min(range(_KEEP_SLOTS), key=lambda i: tokens[i])
+
+
 class _GenFn(torch.autograd.Function):
     """netG(x) on the native engine. `anchor` (a parameter) only makes autograd schedule backward(); the
     parameter gradients are written by the engine as a side effect, the way fused optimisers consume them."""
@@ -46,7 +57,6 @@ class NativeSkip(nn.Sequential):
         self._flat_grad: Optional[torch.Tensor] = None
         self._grad_views: List[torch.Tensor] = []
         self._slot_tokens = [None] * 4
-        self._next_slot = 0
         self._token = 0
 
     # ---- pointer tables ----------------------------------------------------------------------------
@@ -127,14 +137,7 @@ class NativeSkip(nn.Sequential):
         n, _, h, w = x.shape
         out = torch.empty_like(x)
         if keep:
-            # lowest free slot: the same call site gets the same slot every step (x_global -> 0, y_global -> 1, ...),
-            # which keeps the engine's (slot, shape) CUDA-graph keys few; a never-backwarded pass is recycled last
-            free = [i for i in range(_KEEP_SLOTS) if self._slot_tokens[i] is None]
-            if free:
-                slot = free[0]
-            else:
-                slot = self._next_slot
-                self._next_slot = (self._next_slot + 1) % _KEEP_SLOTS
+            slot = pick_keep_slot(self._slot_tokens)
         else:
             slot = 3
         self._token += 1

@@ -133,3 +133,28 @@ def test_install_as_reference_modules_aliases_every_mirror():
             "from models.extractor import VitExtractor, attn_cosine_sim; print('ok')")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(Path(__file__).resolve().parents[1]))
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_generator_slot_policy_over_the_reference_step_schedule():
+    """Replays the loop's netG call pattern (models/model.py:12-25 + which outputs each step's loss consumes,
+    util/losses.py:34-72): step 0 never backwards y_global, steps = 0 mod 75 keep three passes alive. No pass of
+    the current step may be overwritten before its backward."""
+    from splice_b200.generator import pick_keep_slot
+
+    tokens, tok = [None] * 4, 0
+    for step in range(0, 160):
+        entire = step % 75 == 0
+        calls = ["x_global"] + (["x_entire"] if entire else []) + ["y_global"]
+        used = {"x_global", "x_entire"} if step == 0 else set(calls)
+        live = {}
+        for name in calls:
+            slot = pick_keep_slot(tokens)
+            assert slot not in live.values(), (step, name, slot)
+            tok += 1
+            tokens[slot] = tok
+            live[name] = slot
+        for name in calls:
+            if name in used:
+                tokens[live[name]] = None
+    # steady state: the call site -> slot mapping is stable (few CUDA-graph keys)
+    assert pick_keep_slot(tokens) == 0
