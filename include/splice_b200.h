@@ -181,10 +181,19 @@ SPLICE_API int splice_gen_destroy(void* ctx);
 /* out[N,3,H,W] = netG(x[N,3,H,W]); keep != 0 retains the activations in `slot` (0..3) for splice_gen_backward */
 SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const void* x, int N, int H, int W, void* out,
                                   int slot, int keep, int update_running, void* stream);
+/* Applies the batch statistics the last splice_gen_forward(update_running = 0) left in `slot` to the BatchNorm running
+ * buffers (nn.BatchNorm2d momentum 0.1, unbiased variance, num_batches_tracked += 1). Callers that issue several forward
+ * passes on parallel streams use this afterwards, in call order, to reproduce the reference's sequential updates. */
+SPLICE_API int splice_gen_update_running(void* ctx, const SpliceGenPointers* p, int slot, void* stream);
 /* 1 (default) = replay CUDA graphs keyed by (slot, shape, pointer table); 0 = always launch eagerly */
 SPLICE_API int splice_gen_set_graphs(void* ctx, int on);
-/* parameter gradients += d loss / d params given dout[N,3,H,W] = d loss / d out of the forward kept in `slot` */
-SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream);
+/* parameter gradients of the forward kept in `slot`, given dout[N,3,H,W] = d loss / d out (ref: loss.backward(), train.py:78).
+ * accumulate != 0: p->grad += (autograd's accumulation over the 2-3 netG calls of a step); accumulate == 0: p->grad = (every
+ * element is written). Calls on different slots may run concurrently on different streams when given disjoint grad tables. */
+SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, int accumulate, void* stream);
+/* dst[i] += srcs[0][i] + ... + srcs[n_src-1][i] (fp32, fixed order, n_src <= 4): folds the per-call gradient buffers of
+ * concurrently executed netG backward passes into .grad (ref: autograd gradient accumulation, train.py:56,78) */
+SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, size_t n, void* stream);
 
 /* ---- optimiser -------------------------------------------------------------------------------------- */
 /* One Adam step over n_tensors fp32 tensors (host arrays of device pointers / element counts).

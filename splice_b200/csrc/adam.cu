@@ -36,6 +36,21 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamTable tab, float lr_over_
     }
 }
 
+__global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ dst, AccTable t, int n_src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        float v = dst[i];
+        for (int k = 0; k < n_src; ++k) v += t.src[k][i];
+        dst[i] = v;
+    }
+}
+
+int accumulate_f32(float* dst, const AccTable& t, int n_src, size_t n, cudaStream_t stream) {
+    const size_t blocks = (n + 255) / 256;
+    accumulate_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(dst, t, n_src, n);
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
 int adam_step(const AdamTable& tab, int n_tensors, int max_n, float lr_over_bc1, float inv_bc2_sqrt, float b1, float b2,
               float eps, cudaStream_t stream) {
     SPLICE_REQUIRE(n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "adam: n_tensors %d out of range", n_tensors);

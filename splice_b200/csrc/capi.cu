@@ -282,17 +282,30 @@ SPLICE_API int splice_gen_forward(void* ctx, const SpliceGenPointers* p, const v
     return static_cast<GenEngine*>(ctx)->forward(g, (const float*)x, N, H, W, (float*)out, slot, keep != 0, update_running != 0,
                                                  (cudaStream_t)stream);
 }
+SPLICE_API int splice_gen_update_running(void* ctx, const SpliceGenPointers* p, int slot, void* stream) {
+    SPLICE_REQUIRE(ctx && p, "splice_gen_update_running: null argument");
+    GenPointers g;
+    to_gen_ptrs(p, &g);
+    return static_cast<GenEngine*>(ctx)->update_running_stats(g, slot, (cudaStream_t)stream);
+}
 SPLICE_API int splice_gen_set_graphs(void* ctx, int on) {
     SPLICE_REQUIRE(ctx, "splice_gen_set_graphs: null ctx");
     static_cast<GenEngine*>(ctx)->set_graphs(on != 0);
     return SPLICE_OK;
 }
-SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, void* stream) {
+SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, int accumulate, void* stream) {
     SPLICE_REQUIRE(ctx && p, "splice_gen_backward: null argument");
     GenPointers g;
     to_gen_ptrs(p, &g);
     for (int i = 0; i < GEN_PARAMS; ++i) SPLICE_REQUIRE(g.param[i] && g.grad[i], "splice_gen_backward: parameter/grad %d is null", i);
-    return static_cast<GenEngine*>(ctx)->backward(g, (const float*)dout, slot, (cudaStream_t)stream);
+    return static_cast<GenEngine*>(ctx)->backward(g, (const float*)dout, slot, accumulate != 0, (cudaStream_t)stream);
+}
+SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, size_t n, void* stream) {
+    SPLICE_REQUIRE(dst && srcs && n_src > 0 && n_src <= ACC_MAX_SRC && n > 0, "splice_accumulate: bad argument");
+    AccTable t;
+    for (int i = 0; i < ACC_MAX_SRC; ++i) t.src[i] = i < n_src ? (const float*)srcs[i] : nullptr;
+    for (int i = 0; i < n_src; ++i) SPLICE_REQUIRE(t.src[i], "splice_accumulate: source %d is null", i);
+    return accumulate_f32((float*)dst, t, n_src, n, (cudaStream_t)stream);
 }
 
 // ---- optimiser -----------------------------------------------------------------------------------

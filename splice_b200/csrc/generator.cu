@@ -199,8 +199,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) conv_finish_bn_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
                                                              float* __restrict__ y, int N, int C, int HW,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                             float4* __restrict__ konst, float* running_mean, float* running_var,
-                                                             long long* nbt, float momentum) {
+                                                             float4* __restrict__ konst, float2* __restrict__ bstat) {
     __shared__ float red[8];
     const int c = blockIdx.x, count = N * HW;
     const size_t total = (size_t)N * C * HW;
@@ -226,11 +225,7 @@ __global__ void __launch_bounds__(256) conv_finish_bn_kernel(const float* __rest
         const float invstd = rsqrtf(var + eps);
         const float g = gamma[c] * invstd;
         konst[c] = make_float4(mean, invstd, g, beta[c] - mean * g);
-        if (running_mean) {
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (count > 1 ? a[0] / (count - 1) : var);
-            if (c == 0 && nbt) *nbt += 1;
-        }
+        if (bstat) bstat[c] = make_float2(mean, count > 1 ? a[0] / (count - 1) : var);
     }
 }
 
@@ -279,11 +274,10 @@ __global__ void __launch_bounds__(256) cat_build_kernel(const float* __restrict_
 }
 
 // merge the per-block (count, mean, M2) partials of one channel (one warp per channel, fixed order),
-// produce (mean, invstd, a, b) and update the running statistics (momentum 0.1, unbiased variance)
+// produce (mean, invstd, a, b) and the batch statistics (mean, unbiased variance) the running-statistics update needs
 __global__ void __launch_bounds__(32) bn_finalize_kernel(const float* __restrict__ part, int nparts, int C,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                         float4* __restrict__ konst, float* running_mean, float* running_var,
-                                                         long long* nbt, float momentum) {
+                                                         float4* __restrict__ konst, float2* __restrict__ bstat) {
     const int c = blockIdx.x, lane = threadIdx.x;
     double n = 0.0, mean = 0.0, M2 = 0.0;
     for (int i = lane; i < nparts; i += 32) {
@@ -314,13 +308,29 @@ __global__ void __launch_bounds__(32) bn_finalize_kernel(const float* __restrict
         const float invstd = (float)(1.0 / sqrt(var + (double)eps));
         const float a = gamma[c] * invstd;
         konst[c] = make_float4((float)mean, invstd, a, beta[c] - (float)mean * a);
-        if (running_mean) {
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-            const double unbiased = n > 1.0 ? M2 / (n - 1.0) : var;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-            if (c == 0 && nbt) *nbt += 1;
-        }
+        if (bstat) bstat[c] = make_float2((float)mean, (float)(n > 1.0 ? M2 / (n - 1.0) : var));
     }
+}
+
+// nn.BatchNorm2d's running statistics (momentum 0.1, unbiased variance, num_batches_tracked) from the batch statistics
+// a forward pass left in its slot. A separate launch so that netG calls issued on parallel streams can apply their
+// updates afterwards in call order, as the reference's sequential calls do (they never influence outputs: the
+// reference never calls .eval(); kept for state_dict() fidelity). One block per BatchNorm layer.
+struct RunningTable {
+    const float2* bstat[GEN_BN];
+    float* rmean[GEN_BN];
+    float* rvar[GEN_BN];
+    long long* nbt[GEN_BN];
+    int C[GEN_BN];
+};
+__global__ void __launch_bounds__(160) update_running_kernel(RunningTable t, float momentum) {
+    const int l = blockIdx.x, c = threadIdx.x;
+    if (c < t.C[l]) {
+        const float2 b = t.bstat[l][c];
+        t.rmean[l][c] = (1.f - momentum) * t.rmean[l][c] + momentum * b.x;
+        t.rvar[l][c] = (1.f - momentum) * t.rvar[l][c] + momentum * b.y;
+    }
+    if (c == 0) *t.nbt[l] += 1;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -350,7 +360,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 }
 // dgamma += sum dz*yhat, dbeta += sum dz, (m1, m2) = sums / count
 __global__ void __launch_bounds__(32) bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
-                                                             float* dgamma, float* dbeta, float2* __restrict__ m) {
+                                                             float* dgamma, float* dbeta, float2* __restrict__ m, int accumulate) {
     const int c = blockIdx.x, lane = threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < nparts; i += 32) {
@@ -362,8 +372,8 @@ __global__ void __launch_bounds__(32) bn_bwd_finalize_kernel(const float* __rest
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     if (lane == 0) {
-        if (dgamma) dgamma[c] += (float)s2;
-        if (dbeta) dbeta[c] += (float)s1;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
         m[c] = make_float2((float)(s1 / count), (float)(s2 / count));
     }
 }
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
 // reduce, dgamma/dbeta accumulation, and the in-place dA -> dy rewrite
 __global__ void __launch_bounds__(256) bn_bwd_small_kernel(float* __restrict__ dA, const float* __restrict__ y,
                                                            const float4* __restrict__ konst, int lrelu, int N, int C, int HW,
-                                                           float* dgamma, float* dbeta) {
+                                                           float* dgamma, float* dbeta, int accumulate) {
     __shared__ float red[16];
     const int c = blockIdx.x, count = N * HW;
     const float4 k = konst[c];
@@ -401,8 +411,8 @@ __global__ void __launch_bounds__(256) bn_bwd_small_kernel(float* __restrict__ d
     }
     block_reduce_vec<2>(a, red);
     if (threadIdx.x == 0) {
-        if (dgamma) dgamma[c] += a[1];
-        if (dbeta) dbeta[c] += a[0];
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + a[1];
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a[0];
     }
     const float m1 = a[0] / count, m2 = a[1] / count;
     for (int e = threadIdx.x; e < count; e += 256) {
@@ -603,14 +613,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
 }
 // grad_w += sum over chunks, grad_b += sum over chunks (fixed order)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nchunks, size_t nW, int Cout,
-                                                           float* __restrict__ gw, float* __restrict__ gb) {
+                                                           float* __restrict__ gw, float* __restrict__ gb, int accumulate) {
     const size_t i = blockIdx.x * (size_t)256 + threadIdx.x;
     const size_t tot = nW + Cout;
     if (i >= tot) return;
     float s = 0.f;
     for (int c = 0; c < nchunks; ++c) s += part[(size_t)c * tot + i];
-    if (i < nW) gw[i] += s;
-    else gb[i - nW] += s;
+    if (i < nW) gw[i] = (accumulate ? gw[i] : 0.f) + s;
+    else gb[i - nW] = (accumulate ? gb[i - nW] : 0.f) + s;
 }
 
 // adjoint of cat_build for the skip branch: d(s activated) = d(cat)[:, :Cs] placed at the crop offset, zero elsewhere
@@ -685,8 +695,7 @@ static void pick_tiling(int P, int Cfast, int Cslow, size_t out_elems, int* ct, 
 struct BnOut {                 // where the BatchNorm constants / running statistics of a conv's output go
     const float *gamma, *beta;
     float4* konst;
-    float *rmean, *rvar;
-    long long* nbt;
+    float2* bstat;
 };
 
 static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin, int Win, InTf tf, const float* Wt,
@@ -709,13 +718,12 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
 #undef CF
     SPLICE_LAUNCH_CHECK();
     if (!bn) return SPLICE_OK;
-    const float eps = 1e-5f, mom = 0.1f;
+    const float eps = 1e-5f;
     if (sk > 1) {
         conv_finish_bn_kernel<<<Cout, 256, 0, st>>>(split_part, sk, bias, y, N, Cout, Ho * Wo, bn->gamma, bn->beta, eps, bn->konst,
-                                                    bn->rmean, bn->rvar, bn->nbt, mom);
+                                                    bn->bstat);
     } else {
-        bn_finalize_kernel<<<Cout, 32, 0, st>>>(stats_part, (int)grid.x, Cout, bn->gamma, bn->beta, eps, bn->konst, bn->rmean,
-                                                bn->rvar, bn->nbt, mom);
+        bn_finalize_kernel<<<Cout, 32, 0, st>>>(stats_part, (int)grid.x, Cout, bn->gamma, bn->beta, eps, bn->konst, bn->bstat);
     }
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
@@ -771,18 +779,28 @@ GenEngine::GenEngine() {
 }
 
 GenEngine::~GenEngine() {
-    for (auto& s : slots_) cudaFree(s.pool);
-    cudaFree(scratch_);
+    for (auto& s : slots_) {
+        cudaFree(s.pool);
+        cudaFree(s.scratch);
+        if (s.side) cudaStreamDestroy(s.side);
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        if (s.ev_join) cudaEventDestroy(s.ev_join);
+    }
 }
 
-int GenEngine::ensure_scratch(size_t bytes) {
-    if (bytes <= scratch_bytes_) return SPLICE_OK;
+int GenEngine::ensure_scratch(Slot& s, size_t bytes) {
+    if (!s.side) {
+        SPLICE_CHECK_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+        SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    }
+    if (bytes <= s.scratch_bytes) return SPLICE_OK;
     SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
-    cudaFree(scratch_);
-    scratch_ = nullptr;
-    scratch_bytes_ = 0;
-    SPLICE_CHECK_CUDA(cudaMalloc(&scratch_, bytes));
-    scratch_bytes_ = bytes;
+    cudaFree(s.scratch);
+    s.scratch = nullptr;
+    s.scratch_bytes = 0;
+    SPLICE_CHECK_CUDA(cudaMalloc(&s.scratch, bytes));
+    s.scratch_bytes = bytes;
     return SPLICE_OK;
 }
 
@@ -812,6 +830,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     plan((size_t)N * 3 * H * W * 4);  // out copy
     plan((size_t)N * 3 * H * W * 4);  // d(pre-sigmoid)
     plan((size_t)N * 3 * H * W * 4);  // dout copy (stable address for the backward graph)
+    plan((size_t)GEN_BN * BSTAT_STRIDE * sizeof(float2));  // batch statistics (mean, unbiased variance) per BN layer
     if (off > s.pool_bytes) {
         SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
         cudaFree(s.pool);
@@ -835,6 +854,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
     s.out = (float*)nx();
     s.dfin = (float*)nx();
     s.dout_copy = (float*)nx();
+    s.bstat = (float2*)nx();
     s.N = N; s.H = H; s.W = W;
     s.valid = false;
     return SPLICE_OK;
@@ -854,7 +874,7 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
     GRC(configure(s, N, H, W));
     // scratch = [statistics partials | split partial sums | weight-gradient partials]
     const size_t stats_floats = (size_t)ceil_div(N * H * W, CONV_THREADS) * 132 * 3 + (size_t)N * ceil_div(H, TH) * ceil_div(W, TW) * 132 * 3;
-    GRC(ensure_scratch((stats_floats + SPLIT_FLOATS + WGRAD_FLOATS) * sizeof(float) + 4096));
+    GRC(ensure_scratch(s, (stats_floats + SPLIT_FLOATS + WGRAD_FLOATS) * sizeof(float) + 4096));
     s.stats_floats = stats_floats;
     // keep a private copy of the input: the caller's tensor may be freed before backward() (wgrad of scale 0 reads it)
     SPLICE_CHECK_CUDA(cudaMemcpyAsync(s.x_copy, x, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -862,30 +882,51 @@ int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W
 
     if (use_graphs_) {
         KeyHasher k;
-        k.add((uint64_t)11).add((uint64_t)slot).add((uint64_t)N).add((uint64_t)H).add((uint64_t)W).add((uint64_t)update_running)
-            .add(s.pool).add(scratch_);
+        k.add((uint64_t)11).add((uint64_t)slot).add((uint64_t)N).add((uint64_t)H).add((uint64_t)W).add(s.pool).add(s.scratch);
         for (int i = 0; i < GEN_PARAMS; ++i) k.add(p.param[i]);
-        if (update_running)
-            for (int i = 0; i < GEN_BN; ++i) k.add(p.running_mean[i]).add(p.running_var[i]).add(p.num_batches_tracked[i]);
-        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return forward_body(p, s, update_running, cs); }));
+        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return forward_body(p, s, cs); }));
     } else {
-        GRC(forward_body(p, s, update_running, st));
+        GRC(forward_body(p, s, st));
     }
+    s.stats_pending = true;
+    if (update_running) GRC(update_running_stats(p, slot, st));
     SPLICE_CHECK_CUDA(cudaMemcpyAsync(out, s.out, (size_t)N * 3 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     s.valid = keep;
     return SPLICE_OK;
 }
 
-int GenEngine::forward_body(const GenPointers& p, Slot& s, bool update_running, cudaStream_t st) {
+int GenEngine::update_running_stats(const GenPointers& p, int slot, cudaStream_t st) {
+    SPLICE_REQUIRE(slot >= 0 && slot < GEN_SLOTS, "generator: slot out of range");
+    Slot& s = slots_[slot];
+    SPLICE_REQUIRE(s.pool && s.stats_pending, "generator: slot %d holds no forward pass whose batch statistics are unapplied", slot);
+    RunningTable t;
+    const Bn* order[GEN_BN];
+    for (int i = 0; i < GEN_SCALES; ++i) {
+        const Scale& c = sc_[i];
+        const Bn* b[6] = {&c.bs, &c.bd1, &c.bd2, &c.bcat, &c.bc1, &c.bc2};
+        for (int k = 0; k < 6; ++k) order[b[k]->idx] = b[k];
+    }
+    for (int l = 0; l < GEN_BN; ++l) {
+        SPLICE_REQUIRE(p.running_mean[l] && p.running_var[l] && p.num_batches_tracked[l], "generator: BN buffer %d is null", l);
+        t.bstat[l] = s.bstat + (size_t)l * BSTAT_STRIDE;
+        t.rmean[l] = p.running_mean[l]; t.rvar[l] = p.running_var[l]; t.nbt[l] = p.num_batches_tracked[l];
+        t.C[l] = order[l]->c;
+    }
+    update_running_kernel<<<GEN_BN, 160, 0, st>>>(t, 0.1f);
+    SPLICE_LAUNCH_CHECK();
+    s.stats_pending = false;
+    return SPLICE_OK;
+}
+
+int GenEngine::forward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
     const int N = s.N, H = s.H, W = s.W;
     const size_t stats_floats = s.stats_floats;
-    float* part = static_cast<float*>(scratch_);
+    float* part = static_cast<float*>(s.scratch);
     float* split = part + stats_floats;
-    const float eps = 1e-5f, mom = 0.1f;
+    const float eps = 1e-5f;
 
     auto bn_out = [&](const Bn& b, float4* k) {
-        return BnOut{p.param[b.pg], p.param[b.pb], k, update_running ? p.running_mean[b.idx] : nullptr,
-                     update_running ? p.running_var[b.idx] : nullptr, update_running ? p.num_batches_tracked[b.idx] : nullptr};
+        return BnOut{p.param[b.pg], p.param[b.pb], k, s.bstat + (size_t)b.idx * BSTAT_STRIDE};
     };
     auto conv_bn = [&](const Conv& c, const Bn& b, const float* in, int hin, int win, InTf tf, float* y, int ho, int wo,
                        float4* k) -> int {
@@ -923,7 +964,7 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, bool update_running, 
         SPLICE_LAUNCH_CHECK();
         {
             const BnOut bo = bn_out(c.bcat, b.k_cat);
-            bn_finalize_kernel<<<C, 32, 0, st>>>(part, N * (int)grid.x, C, bo.gamma, bo.beta, eps, bo.konst, bo.rmean, bo.rvar, bo.nbt, mom);
+            bn_finalize_kernel<<<C, 32, 0, st>>>(part, N * (int)grid.x, C, bo.gamma, bo.beta, eps, bo.konst, bo.bstat);
             SPLICE_LAUNCH_CHECK();
         }
         GRC(conv_bn(c.c1, c.bc1, b.cat, th, tw, InTf{b.k_cat, 0}, b.c1_raw, th, tw, b.k_c1));
@@ -934,7 +975,7 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, bool update_running, 
     return SPLICE_OK;
 }
 
-int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaStream_t st) {
+int GenEngine::backward(const GenPointers& p, const float* dout, int slot, bool accumulate, cudaStream_t st) {
     SPLICE_REQUIRE(slot >= 0 && slot < GEN_SLOTS, "generator: slot out of range");
     Slot& s = slots_[slot];
     SPLICE_REQUIRE(s.pool && s.valid, "generator backward: slot %d holds no kept forward pass", slot);
@@ -942,19 +983,21 @@ int GenEngine::backward(const GenPointers& p, const float* dout, int slot, cudaS
     SPLICE_CHECK_CUDA(cudaMemcpyAsync(s.dout_copy, dout, (size_t)s.N * 3 * s.H * s.W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (use_graphs_) {
         KeyHasher k;
-        k.add((uint64_t)12).add((uint64_t)slot).add((uint64_t)s.N).add((uint64_t)s.H).add((uint64_t)s.W).add(s.pool).add(scratch_);
+        k.add((uint64_t)12).add((uint64_t)slot).add((uint64_t)s.N).add((uint64_t)s.H).add((uint64_t)s.W).add(s.pool).add(s.scratch)
+            .add((uint64_t)accumulate);
         for (int i = 0; i < GEN_PARAMS; ++i) k.add(p.param[i]).add(p.grad[i]);
-        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return backward_body(p, s, cs); }));
+        GRC(graphs_.run(k.h, st, [&](cudaStream_t cs) { return backward_body(p, s, accumulate, cs); }));
     } else {
-        GRC(backward_body(p, s, st));
+        GRC(backward_body(p, s, accumulate, st));
     }
     s.valid = false;
     return SPLICE_OK;
 }
 
-int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
+int GenEngine::backward_body(const GenPointers& p, Slot& s, bool accumulate, cudaStream_t st) {
     const int N = s.N, H = s.H, W = s.W;
-    float* part = static_cast<float*>(scratch_);
+    const int acc = accumulate ? 1 : 0;
+    float* part = static_cast<float*>(s.scratch);
     float* split = part + s.stats_floats;
     float* wpart = split + SPLIT_FLOATS;
 
@@ -962,14 +1005,14 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
     auto bn_bwd = [&](const Bn& b, float* dA, const float* y, const float4* k, int lrelu, int hh, int ww, float2* m) -> int {
         const int HW = hh * ww;
         if ((size_t)N * HW <= 8192) {
-            bn_bwd_small_kernel<<<b.c, 256, 0, st>>>(dA, y, k, lrelu, N, b.c, HW, p.grad[b.pg], p.grad[b.pb]);
+            bn_bwd_small_kernel<<<b.c, 256, 0, st>>>(dA, y, k, lrelu, N, b.c, HW, p.grad[b.pg], p.grad[b.pb], acc);
             SPLICE_LAUNCH_CHECK();
             return SPLICE_OK;
         }
         dim3 grid(ceil_div(HW, 2048), b.c, N);
         bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dA, y, k, lrelu, b.c, HW, part);
         SPLICE_LAUNCH_CHECK();
-        bn_bwd_finalize_kernel<<<b.c, 32, 0, st>>>(part, N * (int)grid.x, b.c, (double)N * HW, p.grad[b.pg], p.grad[b.pb], m);
+        bn_bwd_finalize_kernel<<<b.c, 32, 0, st>>>(part, N * (int)grid.x, b.c, (double)N * HW, p.grad[b.pg], p.grad[b.pb], m, acc);
         SPLICE_LAUNCH_CHECK();
         const size_t total = (size_t)N * b.c * HW;
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
@@ -977,7 +1020,13 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
+    // Weight gradients hang off the critical path (bn_bwd -> dgrad -> bn_bwd -> ...): each one only needs this layer's dy,
+    // which is complete on `st` when wgrad() is called, so they run on the slot's side stream (a parallel branch of the
+    // captured graph) and are joined at the end of the pass. The side stream is in order, so `wpart` is reused safely.
+    cudaStream_t ws = s.side;
     auto wgrad = [&](const Conv& c, const float* in, int hin, int win, InTf tf, const float* dy, int ho, int wo) -> int {
+        SPLICE_CHECK_CUDA(cudaEventRecord(s.ev_fork, st));
+        SPLICE_CHECK_CUDA(cudaStreamWaitEvent(ws, s.ev_fork, 0));
         const int ntiles = N * ceil_div(ho, TH) * ceil_div(wo, TW);
         const size_t nW = (size_t)c.cout * c.cin * c.k * c.k;
         size_t cap = WGRAD_FLOATS / (nW + c.cout);
@@ -993,13 +1042,13 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
             attr = true;
         }
         if (c.k == 1 && c.stride == 1)
-            conv_wgrad_kernel<1, 1><<<grid, 256, wgrad_smem_floats<1, 1>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<1, 1><<<grid, 256, wgrad_smem_floats<1, 1>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         else if (c.k == 3 && c.stride == 1)
-            conv_wgrad_kernel<3, 1><<<grid, 256, wgrad_smem_floats<3, 1>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<3, 1><<<grid, 256, wgrad_smem_floats<3, 1>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         else
-            conv_wgrad_kernel<3, 2><<<grid, 256, wgrad_smem_floats<3, 2>() * 4, st>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            conv_wgrad_kernel<3, 2><<<grid, 256, wgrad_smem_floats<3, 2>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
         SPLICE_LAUNCH_CHECK();
-        wgrad_reduce_kernel<<<ceil_div((int)(nW + c.cout), 256), 256, 0, st>>>(wpart, chunks, nW, c.cout, p.grad[c.pw], p.grad[c.pb]);
+        wgrad_reduce_kernel<<<ceil_div((int)(nW + c.cout), 256), 256, 0, ws>>>(wpart, chunks, nW, c.cout, p.grad[c.pw], p.grad[c.pb], acc);
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
@@ -1061,6 +1110,8 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
         GRC(wgrad(c.d1, in, b.h, b.w, tf_in, b.dA_d1, b.hd, b.wd));
         if (dIn) GRC(dgrad(c.d1, b.dA_d1, b.hd, b.wd, dIn, b.h, b.w, 1));
     }
+    SPLICE_CHECK_CUDA(cudaEventRecord(s.ev_join, ws));
+    SPLICE_CHECK_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
     return SPLICE_OK;
 }
 

@@ -11,6 +11,7 @@ static constexpr int GEN_SCALES = 5;
 static constexpr int GEN_PARAMS = 112;     // netG.parameters() order (oracle/splice_ref.py generator_param_keys)
 static constexpr int GEN_BN = 30;          // BatchNorm2d layers, module order
 static constexpr int GEN_SLOTS = 4;
+static constexpr int BSTAT_STRIDE = 160;   // >= the widest BatchNorm (132 channels)
 
 struct GenPointers {
     float* param[GEN_PARAMS];
@@ -27,8 +28,13 @@ public:
     // x [N,3,H,W] -> out [N,3,H,W] (sigmoid). keep = activations stay in `slot` for backward().
     int forward(const GenPointers& p, const float* x, int N, int H, int W, float* out, int slot, bool keep,
                 bool update_running, cudaStream_t stream);
-    // dout [N,3,H,W] -> parameter gradients accumulated into p.grad; dx (optional) = d loss / d input
-    int backward(const GenPointers& p, const float* dout, int slot, cudaStream_t stream);
+    // dout [N,3,H,W] -> parameter gradients: p.grad += (accumulate) or p.grad = (overwrite, every element is written).
+    // Calls on different slots may be in flight on different streams at once (each slot owns its scratch); they must
+    // then be given disjoint gradient tables (overwrite mode + splice_accumulate afterwards).
+    int backward(const GenPointers& p, const float* dout, int slot, bool accumulate, cudaStream_t stream);
+    // applies the batch statistics the last forward() left in `slot` to the BatchNorm running buffers (momentum 0.1);
+    // forward(update_running = true) does this itself, parallel-stream callers pass false and call this in call order
+    int update_running_stats(const GenPointers& p, int slot, cudaStream_t stream);
     void set_graphs(bool on) { use_graphs_ = on; }
 
 private:
@@ -56,21 +62,25 @@ private:
         float* out = nullptr;
         float* dfin = nullptr;
         float* dout_copy = nullptr;
+        float2* bstat = nullptr;
+        bool stats_pending = false;
         size_t stats_floats = 0;
+        void* scratch = nullptr;   // partial-reduction scratch of this slot: [BN statistics | split-K sums | wgrad partials]
+        size_t scratch_bytes = 0;
+        cudaStream_t side = nullptr;            // weight-gradient branch of the backward pass (forked from / joined into
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the caller's stream; becomes a parallel branch under capture)
         ScaleBuf sb[GEN_SCALES];
     };
     int configure(Slot& s, int N, int H, int W);
-    int ensure_scratch(size_t bytes);
+    int ensure_scratch(Slot& s, size_t bytes);
 
     Scale sc_[GEN_SCALES];
     Conv final_;
     Slot slots_[GEN_SLOTS];
-    int forward_body(const GenPointers& p, Slot& s, bool update_running, cudaStream_t st);
-    int backward_body(const GenPointers& p, Slot& s, cudaStream_t st);
+    int forward_body(const GenPointers& p, Slot& s, cudaStream_t st);
+    int backward_body(const GenPointers& p, Slot& s, bool accumulate, cudaStream_t st);
     GraphCache graphs_;
     bool use_graphs_ = true;
-    void* scratch_ = nullptr;      // partial-reduction scratch shared by all calls (stream-ordered reuse)
-    size_t scratch_bytes_ = 0;
 };
 
 }  // namespace splice

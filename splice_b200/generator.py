@@ -31,19 +31,22 @@ def pick_keep_slot(tokens) -> int:
 
 
 class _GenFn(torch.autograd.Function):
-    """netG(x) on the native engine. `anchor` (a parameter) only makes autograd schedule backward(); the
-    parameter gradients are written by the engine as a side effect, the way fused optimisers consume them."""
+    """netG over one or several independent inputs on the native engine (one autograd node for all of them, so that
+    the backward passes of a step's 2-3 netG calls can be issued together). `anchor` (a parameter) only makes
+    autograd schedule backward(); the parameter gradients are written by the engine as a side effect, the way
+    fused optimisers consume them."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, anchor: torch.Tensor, module: "NativeSkip", keep: bool):
-        out, slot, token = module._run_forward(x, keep)
-        ctx.module, ctx.slot, ctx.token = module, slot, token
-        return out
+    def forward(ctx, anchor: torch.Tensor, module: "NativeSkip", keep: bool, *xs: torch.Tensor):
+        outs, slots, tokens = module._run_forward(xs, keep)
+        ctx.module, ctx.slots, ctx.tokens = module, slots, tokens
+        ctx.set_materialize_grads(False)   # an output no loss term consumed arrives as None: its backward is skipped
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, gout: torch.Tensor):
-        ctx.module._run_backward(gout, ctx.slot, ctx.token)
-        return None, None, None, None
+    def backward(ctx, *gouts):
+        ctx.module._run_backward(gouts, ctx.slots, ctx.tokens)
+        return (None, None, None) + (None,) * len(gouts)
 
 
 class NativeSkip(nn.Sequential):
@@ -58,6 +61,10 @@ class NativeSkip(nn.Sequential):
         self._grad_views: List[torch.Tensor] = []
         self._slot_tokens = [None] * 4
         self._token = 0
+        self._side_streams: List[torch.cuda.Stream] = []
+        self._priv_grads: List[torch.Tensor] = []     # per-slot gradient buffers of concurrently issued backward passes
+        self._priv_ptrs: dict = {}
+        self.concurrent = True                        # independent netG calls of a step run on parallel streams
 
     # ---- pointer tables ----------------------------------------------------------------------------
     def _param_list(self) -> List[torch.nn.Parameter]:
@@ -113,6 +120,11 @@ class NativeSkip(nn.Sequential):
                 off += p.numel()
             for p, v in zip(ps, self._grad_views):
                 p._splice_flat_grad, p._splice_grad_view = self._flat_grad, v
+        for p, v in zip(ps, self._grad_views):   # a gradient tensor somebody else assigned: adopt its value, keep our view
+            if p.grad is not None and p.grad is not v:
+                v.copy_(p.grad)
+                p.grad = v
+                self._ptr_sig = None
         missing = [i for i, p in enumerate(ps) if p.grad is None]
         if len(missing) == len(ps):
             self._flat_grad.zero_()
@@ -126,44 +138,120 @@ class NativeSkip(nn.Sequential):
             self._ptr_sig = None
 
     # ---- execution ---------------------------------------------------------------------------------
-    def _run_forward(self, x: torch.Tensor, keep: bool):
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError("netG expects [N,3,H,W]")
-        x = x.detach()
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
-        if not x.is_cuda:
-            raise RuntimeError("the native generator runs on sm_100a only; there is no CPU fallback")
-        n, _, h, w = x.shape
-        out = torch.empty_like(x)
-        if keep:
-            slot = pick_keep_slot(self._slot_tokens)
-        else:
-            slot = 3
-        self._token += 1
-        self._slot_tokens[slot] = self._token
+    def _streams(self, n: int) -> List[torch.cuda.Stream]:
+        while len(self._side_streams) < n:
+            self._side_streams.append(torch.cuda.Stream())
+        return self._side_streams[:n]
+
+    def _private_table(self, slot: int):
+        """Pointer table whose gradients point into this slot's private flat buffer (overwrite-mode backward)."""
+        ps = self._param_list()
+        key = (slot, ps[0].data_ptr(), ps[-1].data_ptr())
+        hit = self._priv_ptrs.get(slot)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        while len(self._priv_grads) <= slot:
+            self._priv_grads.append(torch.empty_like(self._flat_grad))
+        flat = self._priv_grads[slot]
+        t = _lib.SpliceGenPointers()
+        off = 0
+        for i, p in enumerate(ps):
+            t.param[i] = p.data_ptr()
+            t.grad[i] = flat.data_ptr() + 4 * off
+            off += p.numel()
+        self._priv_ptrs[slot] = (key, t, flat)
+        return t, flat
+
+    def _run_forward(self, xs, keep: bool):
+        prepared = []
+        for x in xs:
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise ValueError("netG expects [N,3,H,W]")
+            x = x.detach()
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            if not x.is_cuda:
+                raise RuntimeError("the native generator runs on sm_100a only; there is no CPU fallback")
+            prepared.append(x)
+        if not keep and len(prepared) > 1:
+            raise RuntimeError("several no-grad netG calls share one activation slot: call them one at a time")
         t = self._refresh_ptrs(need_grads=False)
-        check(_lib.splice_gen_forward(self._engine(), C.byref(t), x.data_ptr(), n, h, w, out.data_ptr(), slot,
-                                      1 if keep else 0, 1 if self.training else 0, cur_stream()), "splice_gen_forward")
-        return out, slot, self._token
+        main = torch.cuda.current_stream()
+        side = self._streams(len(prepared)) if (self.concurrent and len(prepared) > 1) else None
+        outs, slots, tokens = [], [], []
+        for k, x in enumerate(prepared):
+            n, _, h, w = x.shape
+            out = torch.empty_like(x)
+            slot = pick_keep_slot(self._slot_tokens) if keep else 3
+            self._token += 1
+            self._slot_tokens[slot] = self._token
+            if side is not None:
+                side[k].wait_stream(main)
+                stream = side[k].cuda_stream
+            else:
+                stream = main.cuda_stream
+            update_now = self.training and side is None
+            check(_lib.splice_gen_forward(self._engine(), C.byref(t), x.data_ptr(), n, h, w, out.data_ptr(), slot,
+                                          1 if keep else 0, 1 if update_now else 0, stream), "splice_gen_forward")
+            outs.append(out); slots.append(slot); tokens.append(self._token)
+        if side is not None:
+            for st in side:
+                main.wait_stream(st)
+            if self.training:   # running statistics: applied in call order, like the reference's sequential calls
+                for slot in slots:
+                    check(_lib.splice_gen_update_running(self._engine(), C.byref(t), slot, main.cuda_stream),
+                          "splice_gen_update_running")
+        return outs, slots, tokens
 
-    def _run_backward(self, gout: torch.Tensor, slot: int, token: int):
-        if self._slot_tokens[slot] != token:
-            raise RuntimeError("generator activations were overwritten: more than 3 netG calls were kept alive "
-                               "before their backward pass")
-        gout = gout.detach()
-        if gout.dtype != torch.float32 or not gout.is_contiguous():
-            gout = gout.float().contiguous()
+    def _run_backward(self, gouts, slots, tokens):
+        live = []
+        for gout, slot, token in zip(gouts, slots, tokens):
+            if self._slot_tokens[slot] != token:
+                raise RuntimeError("generator activations were overwritten: more than 3 netG calls were kept alive "
+                                   "before their backward pass")
+            self._slot_tokens[slot] = None
+            if gout is None:
+                continue
+            gout = gout.detach()
+            if gout.dtype != torch.float32 or not gout.is_contiguous():
+                gout = gout.float().contiguous()
+            live.append((gout, slot))
+        if not live:
+            return
         self._attach_grads()
-        t = self._refresh_ptrs(need_grads=True)
-        check(_lib.splice_gen_backward(self._engine(), C.byref(t), gout.data_ptr(), slot, cur_stream()),
-              "splice_gen_backward")
-        self._slot_tokens[slot] = None
+        main = torch.cuda.current_stream()
+        if len(live) == 1 or not self.concurrent:
+            t = self._refresh_ptrs(need_grads=True)
+            for gout, slot in live:
+                check(_lib.splice_gen_backward(self._engine(), C.byref(t), gout.data_ptr(), slot, 1, main.cuda_stream),
+                      "splice_gen_backward")
+            return
+        # independent passes: each on its own stream into its own gradient buffer, then one fold into .grad
+        side = self._streams(len(live))
+        privs = []
+        for (gout, slot), st in zip(live, side):
+            t, flat = self._private_table(slot)
+            st.wait_stream(main)
+            check(_lib.splice_gen_backward(self._engine(), C.byref(t), gout.data_ptr(), slot, 0, st.cuda_stream),
+                  "splice_gen_backward")
+            privs.append(flat)
+        for st in side:
+            main.wait_stream(st)
+        srcs = (C.c_void_p * len(privs))(*[f.data_ptr() for f in privs])
+        check(_lib.splice_accumulate(self._flat_grad.data_ptr(), srcs, len(privs), self._flat_grad.numel(), main.cuda_stream),
+              "splice_accumulate")
 
-    def forward(self, input):
+    def forward_many(self, inputs):
+        """[netG(x) for x in inputs] — the independent netG calls of one step (models/model.py:16-23), issued together."""
+        inputs = list(inputs)
         anchor = next(self.parameters())
         keep = torch.is_grad_enabled() and anchor.requires_grad   # (grad mode is off inside Function.forward)
-        return _GenFn.apply(input, anchor, self, keep)
+        if not keep:
+            return [_GenFn.apply(anchor, self, False, x)[0] for x in inputs]
+        return list(_GenFn.apply(anchor, self, True, *inputs))
+
+    def forward(self, input):
+        return self.forward_many([input])[0]
 
     def forward_reference_ops(self, input):
         """The same tree evaluated module by module with torch ops (tests only: isolates engine bugs)."""

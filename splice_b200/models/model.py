@@ -16,10 +16,14 @@ class Model(torch.nn.Module):
     def forward(self, input):
         """{'x_global': netG(A_global), ['x_entire': netG(A)], 'y_global': netG(B_global)} (ref model.py:12-25)."""
         cfg = self.cfg
-        outputs = {}
+        calls = []
         if cfg['lambda_global_cls'] + cfg['lambda_global_ssim'] > 0:
-            outputs['x_global'] = self.netG(input['A_global'])
+            calls.append(('x_global', input['A_global']))
         if cfg['lambda_entire_ssim'] > 0 and float(input['step']) % cfg['entire_A_every'] == 0:
-            outputs['x_entire'] = self.netG(input['A'])
-        outputs['y_global'] = self.netG(input['B_global'])
-        return outputs
+            calls.append(('x_entire', input['A']))
+        calls.append(('y_global', input['B_global']))
+        # the 2-3 calls are independent (each has its own BatchNorm batch statistics): the native generator issues
+        # them on parallel streams; running statistics are updated in call order like the reference's sequential calls
+        many = getattr(self.netG, 'forward_many', None)
+        outs = many([x for _, x in calls]) if many is not None else [self.netG(x) for _, x in calls]
+        return {name: out for (name, _), out in zip(calls, outs)}

@@ -691,6 +691,54 @@ def generator_native_small():
 
 
 @check
+def generator_concurrent_calls():
+    """forward_many (parallel streams, per-call gradient buffers, wgrad side branch, graph replay from the 3rd round on)
+    must reproduce the same calls issued one after the other: outputs and running statistics bit for bit, accumulated
+    gradients up to the order of the fp32 additions (autograd runs the sequential backward passes last-to-first, the
+    fold adds the per-call buffers first-to-last; two live calls commute exactly, three differ by an ulp)."""
+    import copy
+    import torch
+
+    from splice_b200.models.networks import define_G
+
+    torch.manual_seed(3)
+    a = define_G("xavier", 0.02).cuda()
+    with torch.no_grad():
+        for p in a.parameters():
+            if p.dim() == 4:
+                p.mul_(20.0)
+    b = copy.deepcopy(a)
+    b.concurrent = False
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(1, 3, 120, 117), (1, 3, 128, 128), (1, 3, 97, 101)]
+    out = []
+    for rnd in range(4):
+        xs = [torch.rand(s, device="cuda", generator=g) for s in shapes]
+        gs = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+        use = [True, rnd != 1, True]      # round 1: the middle output feeds no loss term (its backward is skipped)
+        for net in (a, b):
+            for p in net.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+        oa = a.forward_many(xs)
+        ob = [b(x) for x in xs]
+        sum((o * w).sum() for o, w, u in zip(oa, gs, use) if u).backward()
+        sum((o * w).sum() for o, w, u in zip(ob, gs, use) if u).backward()
+        torch.cuda.synchronize()
+        r = {"round": rnd,
+             "out_maxabs": max(_maxabs(x, y) for x, y in zip(oa, ob)),
+             "grad_maxabs": max(_maxabs(p.grad, q.grad) for p, q in zip(a.parameters(), b.parameters())),
+             "grad_norm": sum(p.grad.norm().item() for p in a.parameters()),
+             "grad_rel_max": max(_maxabs(p.grad, q.grad) / max(q.grad.abs().max().item(), 1e-30)
+                                 for p, q in zip(a.parameters(), b.parameters())),
+             "buffers_maxabs": max(_maxabs(x.float(), y.float()) for x, y in zip(a.buffers(), b.buffers()))}
+        r["ok"] = (r["out_maxabs"] == 0.0 and r["buffers_maxabs"] == 0.0 and r["grad_norm"] > 0
+                   and (r["grad_maxabs"] == 0.0 if sum(use) == 2 else r["grad_rel_max"] < 1e-6))
+        out.append(r)
+    return out
+
+
+@check
 def generator_native_224():
     return [_generator_case(1, 224, 224), _generator_case(1, 213, 213)]
 
