@@ -113,7 +113,7 @@ typedef struct SpliceVitForwardArgs {
     int out_h, out_w;      /* resize target = ViT input size; trailing out % patch pixels are dropped like the patch conv does */
     const void* pos;       /* fp32 [1 + gh*gw, D] interpolated pos_embed, NULL = trained grid */
     int n_grad;            /* activations of the first n_grad images are kept for splice_vit_backward */
-    int slot;              /* 0 or 1: two forward passes may be alive before their backward */
+    int slot;              /* 0..7: activation slot; passes in different slots may be alive (or in flight on different streams) at once */
     void* keys32;          /* out fp32 [n_images*t, D]: layer-11 keys (head h at columns h*64..), or NULL */
     void* cls32;           /* out fp32 [n_images, D]: block-11 output token 0 (pre final norm), or NULL */
     void* qkv32_all;       /* out fp32 [depth, n_images*t, 3D] (compat taps), or NULL */

@@ -143,6 +143,7 @@ __device__ __forceinline__ void store_acc_bf16(bf16* __restrict__ dst, int ld, i
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                        float* __restrict__ lse, int t, int D, float scale_log2) {
     __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];  // Q | K0 | K1 | V0 | V1
+    pdl_sync();
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK[2] = {sQ + TILE_BYTES, sQ + 2 * TILE_BYTES};
     const uint32_t sV[2] = {sQ + 3 * TILE_BYTES, sQ + 4 * TILE_BYTES};
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
                                                           float* __restrict__ delta, bf16* __restrict__ dqkv, int t, int D,
                                                           float scale, float scale_log2) {
     __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];  // Q(then dO) | K0 | K1 | V0 | V1
+    pdl_sync();
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK[2] = {sQ + TILE_BYTES, sQ + 2 * TILE_BYTES};
     const uint32_t sV[2] = {sQ + 3 * TILE_BYTES, sQ + 4 * TILE_BYTES};
@@ -349,6 +351,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restric
     __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES];  // Q0 | Q1 | dO0 | dO1  (K, V staged in Q1 / dO1 first)
     __shared__ float s_lse[2][TK];
     __shared__ float s_dl[2][TK];
+    pdl_sync();
     const uint32_t s0 = smem_u32(smem);
     const uint32_t sQ[2] = {s0, s0 + TILE_BYTES};
     const uint32_t sdO[2] = {s0 + 2 * TILE_BYTES, s0 + 3 * TILE_BYTES};
@@ -446,7 +449,7 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, int S, int t, int D, int
     if (rc) return rc;
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     dim3 grid(ceil_div(t, TQ), H, S);
-    attn_fwd_kernel<<<grid, 128, 0, stream>>>(qkv, o, lse, t, D, scale_log2);
+    SPLICE_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(128), 0, stream, qkv, o, lse, t, D, scale_log2));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
@@ -457,9 +460,9 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
     if (rc) return rc;
     const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
     dim3 grid(ceil_div(t, TQ), H, S);
-    attn_bwd_dq_kernel<<<grid, 128, 0, stream>>>(qkv, o, dout, lse, delta, dqkv, t, D, scale, scale_log2);
+    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(128), 0, stream, qkv, o, dout, lse, delta, dqkv, t, D, scale, scale_log2));
     SPLICE_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<<<grid, 128, 0, stream>>>(qkv, dout, lse, delta, dqkv, t, D, scale, scale_log2);
+    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(128), 0, stream, qkv, dout, lse, delta, dqkv, t, D, scale, scale_log2));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

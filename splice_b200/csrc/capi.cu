@@ -3,6 +3,7 @@
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -32,6 +33,14 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* v = getenv("SPLICE_B200_PDL");
+        on = (v && v[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 
 }  // namespace splice
 
@@ -132,7 +141,7 @@ SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* a, void
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, void* stream) {
     SPLICE_REQUIRE(ctx && a && a->grads, "splice_vit_backward: null argument");
     VitEngine* e = static_cast<VitEngine*>(ctx);
-    SPLICE_REQUIRE(a->slot >= 0 && a->slot < 4, "splice_vit_backward: slot must be in [0,4)");
+    SPLICE_REQUIRE(a->slot >= 0 && a->slot < VIT_SLOTS, "splice_vit_backward: slot must be in [0,%d)", VIT_SLOTS);
     const int n = e->slot_n_grad(a->slot);
     SPLICE_REQUIRE(n > 0 && n <= 64, "splice_vit_backward: slot %d holds no forward pass with n_grad > 0", a->slot);
     ImageGradRef g[64];

@@ -57,10 +57,42 @@ void count_launch(int n = 1);  // every kernel launch of this library is counted
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): kernels of one dependency chain are launched with the
+// programmaticStreamSerialization attribute, so the next kernel's CTAs are scheduled (and run their prologue:
+// barrier init, TMEM allocation, descriptor prefetch, index math) while the previous kernel drains, instead of
+// paying a full launch latency per node of the replayed graph. Contract for every kernel launched through
+// launch_pdl(): it executes pdl_wait() before its first global-memory access (and before any early return), which
+// blocks until the preceding kernel has completed and flushed — so ordering stays transitive along the chain.
+bool pdl_enabled();   // capi.cu (SPLICE_B200_PDL=0 turns the attribute off)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------
+// PDL device side: wait for the preceding grid (no-op when launched without the attribute), then let the next grid's
+// CTAs be scheduled as soon as this grid's CTAs are all resident or done.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -12,6 +12,7 @@ template <bool kStats>
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
                                                      float* __restrict__ stats, int M, int D, float eps) {
+    pdl_sync();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ stats, const float* __restrict__ gamma,
                                                      const float* g_in, float* g_out, bf16* __restrict__ g16, int M, int D) {
+    pdl_sync();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -113,12 +115,14 @@ __global__ void cast_kernel(const float4* __restrict__ src, uint2* __restrict__ 
 
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int t,
                                 int D) {
+    pdl_sync();
     const int s = blockIdx.x;
     for (int c = threadIdx.x; c < D; c += blockDim.x) x[(size_t)s * t * D + c] = cls[c] + pos[c];
 }
 
 __global__ void add_cols_kernel(bf16* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int lds, int rows,
                                 int cols) {
+    pdl_sync();
     const int c2 = cols >> 1;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * c2; i += (size_t)gridDim.x * blockDim.x) {
         const int r = i / c2, c = (i % c2) * 2;
@@ -134,9 +138,9 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
     SPLICE_REQUIRE(M > 0 && D % 128 == 0 && D <= 128 * LN_MAX_V4, "layernorm: D=%d must be a multiple of 128, <= %d", D,
                    128 * LN_MAX_V4);
     if (stats)
-        ln_fwd_kernel<true><<<ceil_div(M, 4), 128, 0, stream>>>(x, gamma, beta, y16, stats, M, D, eps);
+        SPLICE_CHECK_CUDA(launch_pdl(ln_fwd_kernel<true>, dim3(ceil_div(M, 4)), dim3(128), 0, stream, x, gamma, beta, y16, stats, M, D, eps));
     else
-        ln_fwd_kernel<false><<<ceil_div(M, 4), 128, 0, stream>>>(x, gamma, beta, y16, nullptr, M, D, eps);
+        SPLICE_CHECK_CUDA(launch_pdl(ln_fwd_kernel<false>, dim3(ceil_div(M, 4)), dim3(128), 0, stream, x, gamma, beta, y16, (float*)nullptr, M, D, eps));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
@@ -145,7 +149,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* stats, const flo
                   bf16* g16, int M, int D, cudaStream_t stream) {
     SPLICE_REQUIRE(M > 0 && D % 128 == 0 && D <= 128 * LN_MAX_V4, "layernorm_bwd: D=%d must be a multiple of 128, <= %d", D,
                    128 * LN_MAX_V4);
-    ln_bwd_kernel<<<ceil_div(M, 4), 128, 0, stream>>>(dy, x, stats, gamma, g_in, g_out, g16, M, D);
+    SPLICE_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(ceil_div(M, 4)), dim3(128), 0, stream, dy, x, stats, gamma, g_in, g_out, g16, M, D));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
@@ -160,7 +164,7 @@ int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream)
 }
 
 int write_cls_rows(float* x, const float* cls, const float* pos, int S, int t, int D, cudaStream_t stream) {
-    cls_rows_kernel<<<S, 256, 0, stream>>>(x, cls, pos, t, D);
+    SPLICE_CHECK_CUDA(launch_pdl(cls_rows_kernel, dim3(S), dim3(256), 0, stream, x, cls, pos, t, D));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
@@ -169,7 +173,7 @@ int add_f32_into_bf16_cols(bf16* dst, int ldd, int col0, const float* src, int l
     SPLICE_REQUIRE(cols % 2 == 0 && col0 % 2 == 0 && ldd % 2 == 0 && lds % 2 == 0, "add_cols: even sizes required");
     const size_t n = (size_t)rows * cols / 2;
     const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-    add_cols_kernel<<<blocks, 256, 0, stream>>>(dst, ldd, col0, src, lds, rows, cols);
+    SPLICE_CHECK_CUDA(launch_pdl(add_cols_kernel, dim3(blocks), dim3(256), 0, stream, dst, ldd, col0, src, lds, rows, cols));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

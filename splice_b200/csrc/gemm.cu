@@ -193,6 +193,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_sync();   // everything above overlapped the previous kernel's tail; operands / outputs are touched from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -418,7 +419,8 @@ static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int
     if (rc) return rc;
     const int tiles = ceil_div(N, BN) * ceil_div(M, BM);
     const int grid = tiles < 148 ? tiles : 148;
-    gemm_bf16_tcgen05_persistent_kernel<BN, STAGES><<<grid, 320, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep);
+    SPLICE_CHECK_CUDA(launch_pdl(gemm_bf16_tcgen05_persistent_kernel<BN, STAGES>, dim3(grid), dim3(320), L::TOTAL, stream, tmA, tmB, M, N,
+                                 K, ep));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

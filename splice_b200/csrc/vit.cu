@@ -40,12 +40,14 @@ __global__ void __launch_bounds__(256) convert_weight_kernel(const float* __rest
 }
 
 __global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict__ cls, int t, int D) {
+    pdl_sync();
     const int s = blockIdx.x;
     for (int c = threadIdx.x; c < D; c += blockDim.x) cls[(size_t)s * D + c] = x[(size_t)s * t * D + c];
 }
 
 __global__ void scatter_cls_grad_kernel(float* __restrict__ g, bf16* __restrict__ g16, const float* __restrict__ dcls, int t,
                                         int D) {
+    pdl_sync();
     const int s = blockIdx.x;
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         const float v = dcls[(size_t)s * D + c];
@@ -256,7 +258,7 @@ int VitEngine::profile_read(ProfTotals* out, int n) {
 
 int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
     SPLICE_REQUIRE(a.images && a.n_images > 0, "vit_forward: no images");
-    SPLICE_REQUIRE(a.slot >= 0 && a.slot < 4, "vit_forward: slot must be in [0,4)");
+    SPLICE_REQUIRE(a.slot >= 0 && a.slot < VIT_SLOTS, "vit_forward: slot must be in [0,%d)", VIT_SLOTS);
     SPLICE_REQUIRE(a.n_grad >= 0 && a.n_grad <= a.n_images, "vit_forward: n_grad out of range");
     const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
     SPLICE_REQUIRE(a.out_h >= p && a.out_w >= p, "vit_forward: ViT input %dx%d is smaller than one %d-pixel patch", a.out_h,
@@ -324,14 +326,14 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
                                               cudaMemcpyDeviceToDevice, stream));
     }
     if (a.cls32) {
-        gather_cls_kernel<<<S, 256, 0, stream>>>(s.x0[depth], a.cls32, t, D);
+        SPLICE_CHECK_CUDA(launch_pdl(gather_cls_kernel, dim3(S), dim3(256), 0, stream, (const float*)s.x0[depth], a.cls32, t, D));
         SPLICE_LAUNCH_CHECK();
     }
     return SPLICE_OK;
 }
 
 int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
-    SPLICE_REQUIRE(a.slot >= 0 && a.slot < 4, "vit_backward: slot must be in [0,4)");
+    SPLICE_REQUIRE(a.slot >= 0 && a.slot < VIT_SLOTS, "vit_backward: slot must be in [0,%d)", VIT_SLOTS);
     Slot& s = slots_[a.slot];
     SPLICE_REQUIRE(s.pool && s.n_grad > 0, "vit_backward: slot %d holds no forward pass with n_grad > 0", a.slot);
     SPLICE_REQUIRE(a.grads, "vit_backward: no gradient outputs");
@@ -366,7 +368,7 @@ int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t str
     SPLICE_CHECK_CUDA(cudaMemsetAsync(s.g16, 0, (size_t)Mg * D * sizeof(bf16), stream));
     bool have_g = false;
     if (a.dcls32) {
-        scatter_cls_grad_kernel<<<Sg, 256, 0, stream>>>(s.g, s.g16, a.dcls32, t, D);
+        SPLICE_CHECK_CUDA(launch_pdl(scatter_cls_grad_kernel, dim3(Sg), dim3(256), 0, stream, s.g, s.g16, (const float*)a.dcls32, t, D));
         SPLICE_LAUNCH_CHECK();
         have_g = true;
     }

@@ -12,6 +12,8 @@ struct VitDesc {
     float ln_eps = 1e-6f;
 };
 
+static constexpr int VIT_SLOTS = 8;   // activation slots: forward passes that may be alive (or in flight on parallel streams) at once
+
 struct ImageRef { const float* data; int h, w; };
 struct ImageGradRef { float* data; int h, w; };
 
@@ -89,7 +91,7 @@ private:
     const float *cls_ = nullptr, *pos_ = nullptr, *pe_b_ = nullptr, *norm_g_ = nullptr, *norm_b_ = nullptr;
     const bf16 *pe_w_ = nullptr, *pe_wT_ = nullptr;
     std::vector<LayerW> L_;
-    Slot slots_[4];
+    Slot slots_[VIT_SLOTS];
     void* loss_ws_ = nullptr;
     size_t loss_ws_bytes_ = 0;
     struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };

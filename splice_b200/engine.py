@@ -125,8 +125,12 @@ class VitEngine:
     # ---- forward / backward ------------------------------------------------------------------------
     def forward(self, images: Sequence[torch.Tensor], out_hw: Tuple[int, int], n_grad: int = 0, slot: int = 0,
                 want_keys: bool = True, want_cls: bool = True, want_all_qkv: bool = False,
-                want_all_blocks: bool = False, pre_normalized: bool = False, use_graph: bool = False) -> Dict[str, torch.Tensor]:
+                want_all_blocks: bool = False, pre_normalized: bool = False, use_graph: bool = False,
+                stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """images: fp32 CUDA tensors [3,h,w] in [0,1] (sizes may differ); all are resized to out_hw.
+        `stream` (raw cudaStream_t, default: torch's current stream): passes in different slots may be in flight on
+        different streams; the caller orders the streams (outputs are cached per slot, so no allocation happens here
+        after the first call).
         Returns {'keys': [S,t,D], 'cls': [S,D], 'qkv': [12,S,t,3D], 'block': [12,S,t,D]} (only the requested)."""
         S = len(images)
         oh, ow = out_hw
@@ -166,13 +170,13 @@ class VitEngine:
         a.gemm_impl = self.gemm_impl
         a.pre_normalized = 1 if pre_normalized else 0
         a.use_graph = 1 if use_graph else 0
-        check(_lib.splice_vit_forward(self._ctx, C.byref(a), cur_stream()), "splice_vit_forward")
+        check(_lib.splice_vit_forward(self._ctx, C.byref(a), cur_stream() if stream is None else stream), "splice_vit_forward")
         self._slot_meta[slot] = {"shapes": [(im.shape[1], im.shape[2]) for im in keep[:n_grad]], "t": t, "keep": keep}
         return out
 
     def forward_normalized(self, img: torch.Tensor, **want) -> Dict[str, torch.Tensor]:
         """One already-normalised [3,h,w] image at ViT resolution (the VitExtractor API contract)."""
-        return self.forward([img], (img.shape[1], img.shape[2]), n_grad=0, slot=3, pre_normalized=True, **want)
+        return self.forward([img], (img.shape[1], img.shape[2]), n_grad=0, slot=7, pre_normalized=True, **want)
 
     def grad_buffers(self, slot: int, n_grad: int, t: int):
         """Zeroed (dkeys [n_grad,t,D], dcls [n_grad,D]) with stable addresses (graph replay in backward)."""

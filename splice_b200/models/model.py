@@ -16,6 +16,14 @@ class Model(torch.nn.Module):
     def forward(self, input):
         """{'x_global': netG(A_global), ['x_entire': netG(A)], 'y_global': netG(B_global)} (ref model.py:12-25)."""
         cfg = self.cfg
+        if torch.cuda.is_available():
+            # "inputs are on the device" marker: lets LossG start the targets' ViT pass on a side stream without waiting
+            # for the generator work enqueued below (absent marker = it waits for the whole stream; same results)
+            ready = torch.cuda.Event()
+            ready.record()
+            for v in input.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v._splice_ready = ready
         calls = []
         if cfg['lambda_global_cls'] + cfg['lambda_global_ssim'] > 0:
             calls.append(('x_global', input['A_global']))

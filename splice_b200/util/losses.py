@@ -82,6 +82,8 @@ class LossG(torch.nn.Module):
                                       packed=packed)
         self.engine: VitEngine = self.extractor.engine
         self.global_transform = GlobalTransform(self.engine, cfg['dino_global_patch_size'])
+        self.overlap_targets = True     # targets' ViT pass on a side stream, in the shadow of the generator forward
+        self._side = None
         self.lambdas = dict(
             lambda_global_cls=cfg['lambda_global_cls'],
             lambda_global_ssim=0,
@@ -89,6 +91,11 @@ class LossG(torch.nn.Module):
             lambda_entire_cls=0,
             lambda_global_identity=0
         )
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     # ref losses.py:34-44
     def update_lambda_config(self, step):
@@ -150,15 +157,37 @@ class LossG(torch.nn.Module):
             groups.setdefault(s["hw"], []).append(s)
         if len(groups) > 3:
             raise NotImplementedError("more than 3 distinct ViT input sizes in one step")
-        for slot, (hw, members) in enumerate(groups.items()):
+        main = torch.cuda.current_stream()
+        for g_idx, (hw, members) in enumerate(groups.items()):
             members.sort(key=lambda s: not s["gen"])
             n_grad = sum(1 for s in members if s["gen"])
-            feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot, use_graph=True)
-            t = feats["keys"].shape[1]
+            slot = 2 * g_idx
+            if self.overlap_targets and 0 < n_grad < len(members):
+                # The targets (A_global, B_global, A) do not depend on netG: their no-grad pass goes to a side stream
+                # that only waits for the inputs, so it runs in the shadow of the generator forward the main stream is
+                # still busy with; the generated images follow on the main stream, in their own (kept) slot.
+                gens, tgts = members[:n_grad], members[n_grad:]
+                side = self._side_stream()
+                ready = [getattr(s["batch"], "_splice_ready", None) for s in tgts]
+                if any(e is None for e in ready):
+                    side.wait_stream(main)
+                else:
+                    for e in {id(e): e for e in ready}.values():
+                        side.wait_event(e)
+                ft = eng.forward([s["img"] for s in tgts], hw, n_grad=0, slot=slot + 1, use_graph=True, stream=side.cuda_stream)
+                fg = eng.forward([s["img"] for s in gens], hw, n_grad=n_grad, slot=slot, use_graph=True)
+                main.wait_stream(side)
+                t = fg["keys"].shape[1]
+                parts = [(gens, fg), (tgts, ft)]
+            else:
+                feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot, use_graph=True)
+                t = feats["keys"].shape[1]
+                parts = [(members, feats)]
             dkeys, dcls = eng.grad_buffers(slot, n_grad, t) if n_grad else (None, None)
-            for j, s in enumerate(members):
-                s.update(keys=feats["keys"][j], cls=feats["cls"][j], slot=slot, idx=j,
-                         dkeys=dkeys[j] if s["gen"] else None, dcls=dcls[j] if s["gen"] else None)
+            for part, feats in parts:
+                for j, s in enumerate(part):
+                    s.update(keys=feats["keys"][j], cls=feats["cls"][j], slot=slot, idx=j,
+                             dkeys=dkeys[j] if s["gen"] else None, dcls=dcls[j] if s["gen"] else None)
             members[0]["group"] = {"slot": slot, "n_grad": n_grad, "dkeys": dkeys, "dcls": dcls, "members": members}
 
         # 3. loss kernels: value into terms[k] (summed over crops), gradient into the generated sequence's slot

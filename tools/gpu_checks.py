@@ -528,6 +528,53 @@ def train_step_golden():
 
 
 @check
+def lossg_overlap_targets():
+    """The targets' ViT pass on a side stream (overlapping the generator forward) must give the same objective and the
+    same gradients as the single batched pass on one stream: the rows of a batched GEMM / LayerNorm / attention do not
+    depend on how the sequences are split into launches, so any difference would be a stream-ordering bug."""
+    import torch
+
+    dino_vit, _ = _oracle_on_gpu()
+    from bench import make_cfg, synth_image
+    from splice_b200.models.model import Model
+    from splice_b200.util.losses import LossG
+
+    cfg = make_cfg("dino_vits16")
+    vsd = {k: v.detach() for k, v in dino_vit.build("dino_vits16").state_dict().items()}
+    torch.manual_seed(0)
+    model = Model(cfg)
+    crit = LossG(cfg, state_dict=vsd)
+    A, B = synth_image(1000, 128, 8), synth_image(1001, 128, 16)
+    out = []
+    for step in (0, 1, 2, 3, 75, 76):
+        s = 120 + (step % 5)
+        res = {}
+        for overlap in (True, False):
+            crit.overlap_targets = overlap
+            crit.lambdas.update(lambda_global_ssim=0, lambda_global_identity=0)
+            if step >= 1:
+                crit.update_lambda_config(1)
+            inputs = {"step": torch.tensor([float(step)]), "A_global": A[None, :, :s, :s].contiguous().cuda(),
+                      "B_global": B[None, :, 3:3 + s, 2:2 + s].contiguous().cuda(), "A": A[None].cuda()}
+            for p in model.netG.parameters():
+                p.grad = None
+            outputs = model(inputs)
+            for v in outputs.values():
+                v.retain_grad()
+            losses = crit(outputs, inputs)
+            losses["loss"].backward()
+            torch.cuda.synchronize()
+            res[overlap] = ({k: float(v) for k, v in losses.items()}, {k: v.grad.clone() for k, v in outputs.items() if v.grad is not None})
+        la, lb = res[True][0], res[False][0]
+        r = {"step": step, "terms": sorted(la), "loss": la["loss"],
+             "loss_maxabs": max(abs(la[k] - lb[k]) for k in la),
+             "grad_maxabs": max(_maxabs(res[True][1][k], res[False][1][k]) for k in res[True][1])}
+        r["ok"] = sorted(la) == sorted(lb) and r["loss_maxabs"] == 0.0 and r["grad_maxabs"] == 0.0
+        out.append(r)
+    return out
+
+
+@check
 def adam_kernel():
     import torch
     from splice_b200.optim import FusedAdam
