@@ -145,14 +145,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // warps drain tile i (TMEM -> registers -> fused epilogue -> global), the MMA warp already accumulates tile i+1.
 //   warp 0      TMA producer        warp 1   MMA issuer (+ TMEM alloc/dealloc)       warps 2..9   epilogue
 // Epilogue warp e reads TMEM lane quadrant (warp_id % 4) and the column half (e / 4) of the tile.
+//
+// Thread-block clusters + TMA multicast (CM x CN CTAs per cluster, CM along M, CN along N): measured on B200 the
+// 1-CTA kernel is bound by L2 -> shared-memory operand traffic (~7 TB/s for the whole chip: 128x256 tiles need
+// 96 B/clk/SM, the fabric gives ~25), not by the tensor pipe. A cluster works on a (CM*128) x (CN*BN) super-tile:
+// the CN CTAs of a row share their A tile (each loads 1/CN of its rows and multicasts it to the row), the CM CTAs of a
+// column share their B tile the same way, so every operand byte crosses the L2 fabric once per cluster instead of
+// once per CTA. Pipeline protocol: a stage of CTA X is written by all CTAs of X's row and column ("peers"), so
+//   full_bar[s]  (count 1)            X's own producer arms it with the full stage size; peers' multicasts add bytes
+//   empty_bar[s] (count CM + CN - 1)  every peer's MMA warp commits to it (tcgen05.commit multicast) once its MMAs
+//                                     have read stage s; X's producer may then overwrite stage s in all its peers.
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CM, int CN>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
                                     int N, int K, GemmEpilogue ep) {
     using L = GemmSmem<BN, STAGES>;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static_assert(2 * BN <= 512, "two accumulator stages must fit the 512 TMEM columns");
+    constexpr int CS = CM * CN;                       // cluster size
+    constexpr int A_ROWS = BM / CN, B_ROWS = BN / CM;   // rows of the A / B tile this CTA loads (and multicasts)
+    static_assert(A_ROWS % 8 == 0 && B_ROWS % 8 == 0, "operand slices must be whole 8-row swizzle atoms");
+    static_assert(CS <= 8, "portable cluster size");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -168,8 +182,18 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = K / BK;
-    const int tiles_n = (N + BN - 1) / BN;
-    const int num_tiles = tiles_n * ((M + BM - 1) / BM);
+    // cluster geometry: rank r -> (mi, ni) = (r % CM, r / CM)
+    const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+    const int mi = (int)(crank % CM), ni = (int)(crank / CM);
+    const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+    const int stn = (N + CN * BN - 1) / (CN * BN);
+    const int num_super = stn * ((M + CM * BM - 1) / (CM * BM));
+    uint16_t mask_a = 0, mask_b = 0;                 // receivers of my A slice (my row) / my B slice (my column)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) mask_a |= (uint16_t)(1u << (j * CM + mi));
+#pragma unroll
+    for (int i = 0; i < CM; ++i) mask_b |= (uint16_t)(1u << (ni * CM + i));
+    const uint16_t mask_peers = mask_a | mask_b;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -177,7 +201,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CM + CN - 1);
         }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
@@ -191,6 +215,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_sync();   // everything above overlapped the previous kernel's tail; operands / outputs are touched from here on
@@ -198,15 +223,19 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;   // running k-block counter across tiles (ring position)
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int st = cluster_id; st < num_super; st += num_clusters) {
+                const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_wait(&empty_bar[s], ph ^ 1u);      // all peers' MMAs have read stage s
                     mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-                    tma_load_2d(smemA + s * L::A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
-                    tma_load_2d(smemB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    uint8_t* dA = smemA + s * L::A_BYTES + ni * (A_ROWS * BK * 2);
+                    uint8_t* dB = smemB + s * L::B_BYTES + mi * (B_ROWS * BK * 2);
+                    if constexpr (CN > 1) tma_load_2d_mc(dA, &tmA, &full_bar[s], kb * BK, m0 + ni * A_ROWS, mask_a);
+                    else tma_load_2d(dA, &tmA, &full_bar[s], kb * BK, m0);
+                    if constexpr (CM > 1) tma_load_2d_mc(dB, &tmB, &full_bar[s], kb * BK, n0 + mi * B_ROWS, mask_b);
+                    else tma_load_2d(dB, &tmB, &full_bar[s], kb * BK, n0);
                 }
             }
         }
@@ -214,7 +243,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
             uint32_t it = 0, lt = 0;   // k-block counter, local tile counter
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
                 const uint32_t as = lt & 1u;
                 mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator stage
                 tc_fence_after();
@@ -229,7 +258,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j)
                         umma_bf16_ss(tacc, adesc + 2u * j, bdesc + 2u * j, idesc, (kb | j) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
+                    if constexpr (CS > 1) umma_commit_mc(&empty_bar[s], mask_peers);
+                    else umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&tmem_full_bar[as]);
             }
@@ -240,8 +270,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
         const int half = e >> 2;           // column half of the tile
         constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
+            const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
             const uint32_t as = lt & 1u;
             const int row = m0 + quad * 32 + lane;
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1u);
@@ -250,7 +280,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
             for (int cc = 0; cc < CH_PER_HALF; ++cc) {
                 const int c = half * CH_PER_HALF + cc;
                 const int col = n0 + c * 32;
-                if (c < CHUNKS && col < N) {  // warp-uniform
+                if (c < CHUNKS && col < N && m0 < M) {  // warp-uniform (a padded tile of the super-tile stores nothing)
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
                     tmem_ld_wait();
@@ -270,6 +300,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();   // no CTA exits while a peer may still signal its barriers
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -402,27 +433,76 @@ static int launch_tcgen05(const bf16* A, int lda, const bf16* B, int ldb, int M,
     return SPLICE_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CM, int CN>
 static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep,
                              cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SPLICE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<BN, STAGES>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
-        attr_set = true;
+    constexpr int CS = CM * CN;
+    auto kernel = gemm_bf16_tcgen05_persistent_kernel<BN, STAGES, CM, CN>;
+    static int max_clusters = 0;   // co-resident clusters of this kernel (persistent grid size / CS)
+    if (max_clusters == 0) {
+        SPLICE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        int dev = 0, sms = 148;
+        SPLICE_CHECK_CUDA(cudaGetDevice(&dev));
+        SPLICE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int n = sms / CS;
+        if (CS > 1) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(sms / CS * CS); q.blockDim = dim3(320); q.dynamicSmemBytes = L::TOTAL;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int nc = 0;
+            SPLICE_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &q));
+            SPLICE_REQUIRE(nc > 0, "gemm: no %d-CTA cluster of the %dx%d kernel fits this device", CS, BM, BN);
+            if (nc < n) n = nc;
+        }
+        max_clusters = n;
     }
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM);
+    int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM / CN);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+    rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN / CM);
     if (rc) return rc;
-    const int tiles = ceil_div(N, BN) * ceil_div(M, BM);
-    const int grid = tiles < 148 ? tiles : 148;
-    SPLICE_CHECK_CUDA(launch_pdl(gemm_bf16_tcgen05_persistent_kernel<BN, STAGES>, dim3(grid), dim3(320), L::TOTAL, stream, tmA, tmB, M, N,
-                                 K, ep));
+    const int supers = ceil_div(N, CN * BN) * ceil_div(M, CM * BM);
+    const int clusters = supers < max_clusters ? supers : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CS);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CS > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    SPLICE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, ep));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
+}
+
+// cluster shape used when the caller does not ask for one (bn_hint < 1000): SPLICE_B200_GEMM_CLUSTER="<cm>x<cn>"
+// overrides the built-in choice (tuning aid)
+static void default_cluster(int bn, int M, int N, int* cm, int* cn) {
+    static int env_cm = -1, env_cn = -1;
+    if (env_cm < 0) {
+        env_cm = 0; env_cn = 0;
+        const char* v = getenv("SPLICE_B200_GEMM_CLUSTER");
+        if (v && v[0] >= '1' && v[0] <= '8' && v[1] == 'x' && v[2] >= '1' && v[2] <= '8') { env_cm = v[0] - '0'; env_cn = v[2] - '0'; }
+    }
+    if (env_cm > 0) { *cm = env_cm; *cn = env_cn; return; }
+    (void)bn; (void)M; (void)N;
+    *cm = 1; *cn = 1;
 }
 
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep, int impl,
@@ -461,7 +541,8 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
     }
     SPLICE_REQUIRE(impl == GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
 
-    int bn = bn_hint;
+    // bn_hint = bn + 1000 * cm + 10000 * cn; bn == 0 -> automatic tile width, cm == cn == 0 -> automatic cluster shape
+    int bn = bn_hint % 1000, cm = (bn_hint / 1000) % 10, cn = (bn_hint / 10000) % 10;
     if (bn == 0) {
         // Measured on B200 (tools/gpu_checks.py gemm_tc_timing, ViT-B/8 shapes): the 128x256 tile wins whenever there are
         // enough tiles to occupy the 148 persistent CTAs (it halves the A re-reads through L2, which bound the 128-wide
@@ -470,13 +551,16 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
         else if (N >= 128) bn = 128;
         else bn = 64;
     }
-    switch (bn) {
-        case 64:  return launch_persistent<64, 6>(A, lda, B, ldb, M, N, K, ep, stream);
-        case 128: return launch_persistent<128, 5>(A, lda, B, ldb, M, N, K, ep, stream);
-        case 256: return launch_persistent<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
-        default: break;
-    }
-    set_error("gemm: unsupported BN %d", bn);
+    if (cm == 0 || cn == 0) default_cluster(bn, M, N, &cm, &cn);
+#define SPLICE_GEMM_CASE(BN_, ST_, CM_, CN_) \
+    if (bn == BN_ && cm == CM_ && cn == CN_) return launch_persistent<BN_, ST_, CM_, CN_>(A, lda, B, ldb, M, N, K, ep, stream)
+    SPLICE_GEMM_CASE(64, 6, 1, 1);
+    SPLICE_GEMM_CASE(128, 5, 1, 1); SPLICE_GEMM_CASE(128, 5, 2, 1); SPLICE_GEMM_CASE(128, 5, 1, 2);
+    SPLICE_GEMM_CASE(128, 5, 2, 2); SPLICE_GEMM_CASE(128, 5, 4, 1); SPLICE_GEMM_CASE(128, 5, 4, 2);
+    SPLICE_GEMM_CASE(256, 4, 1, 1); SPLICE_GEMM_CASE(256, 4, 2, 1); SPLICE_GEMM_CASE(256, 4, 1, 2);
+    SPLICE_GEMM_CASE(256, 4, 2, 2); SPLICE_GEMM_CASE(256, 4, 4, 1); SPLICE_GEMM_CASE(256, 4, 4, 2);
+#undef SPLICE_GEMM_CASE
+    set_error("gemm: unsupported tile/cluster BN=%d cluster %dx%d", bn, cm, cn);
     return SPLICE_ERR_ARG;
 }
 

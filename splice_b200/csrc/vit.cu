@@ -344,7 +344,7 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
         RC(backward_body(a, s, stream));
     } else {
         KeyHasher k;
-        k.add((uint64_t)2).add((uint64_t)a.slot).add((uint64_t)Sg).add((uint64_t)t).add(s.pool).add(a.dkeys32).add(a.dcls32)
+        k.add((uint64_t)2).add((uint64_t)a.slot).add((uint64_t)s.S).add((uint64_t)Sg).add((uint64_t)t).add(s.pool).add(a.dkeys32).add(a.dcls32)
             .add((uint64_t)a.gemm_impl);
         RC(graphs_.run(k.h, stream, [&](cudaStream_t st) { return backward_body(a, s, st); }));
     }

@@ -101,6 +101,25 @@ def gemm_tc_multi_tile_edges():
     return out
 
 
+CLUSTER_SHAPES = [(2, 1), (1, 2), (2, 2), (4, 1), (4, 2)]
+
+
+@check
+def gemm_tc_cluster_multicast():
+    """Thread-block-cluster variants (TMA multicast of the shared operand slices, tcgen05.commit multicast on the
+    stage-free barriers): same results as the 1-CTA kernel on full, ragged and padded super-tiles (a super-tile column
+    or row that lies completely outside the matrix still takes part in the loads but stores nothing)."""
+    out = []
+    for (cm, cn) in CLUSTER_SHAPES:
+        for bn in (128, 256):
+            hint = bn + 1000 * cm + 10000 * cn
+            out.append(_gemm_case(3140, 2304, 768, hint))     # forward qkv: many super-tiles per cluster
+            out.append(_gemm_case(785, 768, 3072, hint))      # ragged M, long K (ring wraps many times)
+            out.append(_gemm_case(100, 192, 192, hint))       # single partial tile: the rest of the cluster is padding
+            out.append(_gemm_case(1570, 1280, 64, hint))      # one k-block per tile
+    return out
+
+
 @check
 def gemm_tc_epilogues():
     import torch
@@ -181,8 +200,12 @@ def gemm_tc_timing():
         row = {"M": M, "N": N, "K": K}
         gf = 2.0 * M * N * K / 1e6   # MFLOP -> TFLOP/s = gf / us
         for bn in (64, 128, 256):
-            us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=bn))
+            us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=bn + 11000))
             row[f"persist_bn{bn}"] = round(gf / us, 1)
+        for (cm, cn) in CLUSTER_SHAPES:
+            for bn in (128, 256):
+                us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=bn + 1000 * cm + 10000 * cn))
+                row[f"bn{bn}_c{cm}x{cn}"] = round(gf / us, 1)
         us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=0))
         row["persist_auto"] = round(gf / us, 1)
         us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=128, impl=2))
