@@ -161,6 +161,9 @@ SPLICE_API int splice_loss_mse(void* ctx, const void* a, const void* b, int rows
 SPLICE_API int splice_keys_self_sim(void* ctx, const void* keys, int t, void* out_tt, int gemm_impl, void* stream);
 /* total[0] = sum_i weights_host[i] * terms[i], n <= 8.  ref: LossG.forward util/losses.py:46-72 */
 SPLICE_API int splice_weighted_total(const void* terms, const float* weights_host, int n, void* total, void* stream);
+/* measurement aid: occupy `stream` for ~us microseconds (lets the host enqueue ahead of the device while bench.py
+ * brackets individual kernels with events). No reference counterpart; not on the product path. */
+SPLICE_API int splice_debug_spin(float us, void* stream);
 
 /* ---- generator ------------------------------------------------------------------------------------- */
 /* The default-argument skip() U-Net (ref: models/unet/skip.py:4-102, models/unet/common.py:11-124, called from

@@ -140,6 +140,7 @@ splice_loss_mse = _sig("splice_loss_mse", c_int,
                        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p])
 splice_keys_self_sim = _sig("splice_keys_self_sim", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p])
 splice_weighted_total = _sig("splice_weighted_total", c_int, [c_void_p, C.POINTER(c_float), c_int, c_void_p, c_void_p])
+splice_debug_spin = _sig("splice_debug_spin", c_int, [c_float, c_void_p])
 
 splice_gen_create = _sig("splice_gen_create", c_int, [C.POINTER(c_void_p)])
 splice_gen_destroy = _sig("splice_gen_destroy", c_int, [c_void_p])
@@ -161,7 +162,7 @@ EXPORTS = [
     "splice_layernorm_fwd", "splice_layernorm_bwd", "splice_attention_fwd", "splice_attention_bwd",
     "splice_resized_hw", "splice_preprocess_fwd", "splice_preprocess_bwd", "splice_resize_normalize",
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
-    "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total",
+    "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total", "splice_debug_spin",
     "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward", "splice_gen_set_graphs",
     "splice_accumulate", "splice_gen_update_running",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",

@@ -15,6 +15,9 @@
 // deterministic, no atomics, at the price of recomputing S and dP once.
 #include "attention.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace splice {
 
 static constexpr int HD = 64;       // head dim
@@ -444,9 +447,24 @@ static int check_dims(int S, int t, int D, int H) {
     return SPLICE_OK;
 }
 
+// 0 = tcgen05 kernels (attention_tc.cu, product path); SPLICE_B200_ATTN=legacy | tcfwd | tcbwd selects the mma.sync
+// cross-check kernels for both / the backward / the forward direction (A/B comparison and parity tests)
+static int attn_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* v = getenv("SPLICE_B200_ATTN");
+        mode = 0;
+        if (v && !strcmp(v, "legacy")) mode = 3;
+        else if (v && !strcmp(v, "tcfwd")) mode = 2;   // legacy backward
+        else if (v && !strcmp(v, "tcbwd")) mode = 1;   // legacy forward
+    }
+    return mode;
+}
+
 int attention_fwd(const bf16* qkv, bf16* o, float* lse, int S, int t, int D, int H, cudaStream_t stream) {
     int rc = check_dims(S, t, D, H);
     if (rc) return rc;
+    if (!(attn_mode() & 1)) return attention_fwd_tc(qkv, o, lse, S, t, D, H, stream);
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     dim3 grid(ceil_div(t, TQ), H, S);
     SPLICE_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(128), 0, stream, qkv, o, lse, t, D, scale_log2));
@@ -458,6 +476,7 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
                   int D, int H, cudaStream_t stream) {
     int rc = check_dims(S, t, D, H);
     if (rc) return rc;
+    if (!(attn_mode() & 2)) return attention_bwd_tc(qkv, o, dout, lse, delta, dqkv, S, t, D, H, stream);
     const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
     dim3 grid(ceil_div(t, TQ), H, S);
     SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(128), 0, stream, qkv, o, dout, lse, delta, dqkv, t, D, scale, scale_log2));

@@ -261,6 +261,24 @@ SPLICE_API int splice_weighted_total(const void* terms, const float* weights_hos
     return weighted_total((const float*)terms, weights_host, n, (float*)total, (cudaStream_t)stream);
 }
 
+// Measurement aid (bench.py's per-kernel-class leg): keeps the stream busy for ~us microseconds so that the host can
+// enqueue the eager, event-bracketed launches of a whole step ahead of the device; the events then measure kernel
+// durations, not host enqueue gaps. Not used on the product path.
+__global__ void debug_spin_kernel(long long ns) {
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+SPLICE_API int splice_debug_spin(float us, void* stream) {
+    SPLICE_REQUIRE(us >= 0.f && us <= 1e6f, "splice_debug_spin: %f us out of range", us);
+    debug_spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long)(us * 1e3f));
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
 // ---- generator -----------------------------------------------------------------------------------
 static void to_gen_ptrs(const SpliceGenPointers* p, GenPointers* g) {
     for (int i = 0; i < GEN_PARAMS; ++i) { g->param[i] = (float*)p->param[i]; g->grad[i] = (float*)p->grad[i]; }

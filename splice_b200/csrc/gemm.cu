@@ -379,7 +379,7 @@ static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 static int make_tmap_bf16_uncached(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows);
 
 // 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64, 128B swizzle.
-static int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows) {
+int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows) {
     const TmapKey key{ptr, rows, cols, ld, box_rows};
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     auto it = g_tmaps.find(key);

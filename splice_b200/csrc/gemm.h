@@ -40,6 +40,10 @@ enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1, GEMM_IMPL_TCGEN
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const GemmEpilogue& ep,
                  int impl, int bn_hint, cudaStream_t stream);
 
+// Cached TMA descriptor of a row-major bf16 matrix [rows, cols] (leading dimension ld elements): box = box_rows rows x 64
+// columns (128 bytes), 128B swizzle. Shared with the attention kernels.
+int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows);
+
 #ifdef __CUDACC__
 // Shared epilogue: 32 consecutive accumulator columns [col, col+32) of GEMM row `row`.
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int row, int col, float (&v)[32]) {

@@ -23,6 +23,19 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, maximize=False,
                         foreach=None, capturable=False, differentiable=False, fused=True)
         super().__init__(params, defaults)
+        self._fast = {}   # param-group index -> cached pointer tables + common step count (see step())
+
+    def _flush_fast(self, gi=None):
+        """Write the cached common step count back into the per-parameter state (before anything reads it)."""
+        for k in ([gi] if gi is not None else list(self._fast)):
+            c = self._fast.pop(k, None)
+            if c is not None:
+                for p in c['params']:
+                    self.state[p]['_step'] = c['step']
+
+    def load_state_dict(self, state_dict):
+        self._fast.clear()
+        return super().load_state_dict(state_dict)
 
     def zero_grad(self, set_to_none: bool = True):
         """Gradients that live in the native generator's flat buffer are cleared with ONE memset and stay attached
@@ -50,10 +63,21 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             ps = [p for p in group['params'] if p.grad is not None]
             if not ps:
                 continue
+            # steady state: same parameters, same (flat-buffer) gradient addresses, one common step count -> the ctypes
+            # pointer tables of the previous step are reused and the per-parameter bookkeeping is one integer
+            key = tuple(p.grad.data_ptr() for p in ps)
+            cached = self._fast.get(gi)
+            if cached is not None and cached['key'] == key and all(p.grad.is_contiguous() for p in ps):
+                cached['step'] += 1
+                check(_lib.splice_adam_step(*cached['tables'], cached['n'], cached['step'], float(group['lr']),
+                                            float(group['betas'][0]), float(group['betas'][1]), float(group['eps']),
+                                            cur_stream()), "splice_adam_step")
+                continue
+            self._flush_fast(gi)
             by_step = {}
             for p in ps:
                 st = self.state[p]
@@ -73,18 +97,21 @@ class FusedAdam(torch.optim.Optimizer):
                 n = len(sel)
                 arr = lambda xs: (C.c_void_p * n)(*xs)  # noqa: E731
                 grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in sel]
-                check(_lib.splice_adam_step(
-                    arr([p.data_ptr() for p in sel]), arr([g.data_ptr() for g in grads]),
-                    arr([self.state[p]['exp_avg'].data_ptr() for p in sel]),
-                    arr([self.state[p]['exp_avg_sq'].data_ptr() for p in sel]),
-                    (C.c_int * n)(*[p.numel() for p in sel]), n, step, float(group['lr']),
-                    float(group['betas'][0]), float(group['betas'][1]), float(group['eps']), cur_stream()),
-                    "splice_adam_step")
+                tables = (arr([p.data_ptr() for p in sel]), arr([g.data_ptr() for g in grads]),
+                          arr([self.state[p]['exp_avg'].data_ptr() for p in sel]),
+                          arr([self.state[p]['exp_avg_sq'].data_ptr() for p in sel]),
+                          (C.c_int * n)(*[p.numel() for p in sel]))
+                check(_lib.splice_adam_step(*tables, n, step, float(group['lr']),
+                                            float(group['betas'][0]), float(group['betas'][1]), float(group['eps']),
+                                            cur_stream()), "splice_adam_step")
+                if len(by_step) == 1 and len(sel) == len(ps) and all(g is p.grad for g, p in zip(grads, sel)):
+                    self._fast[gi] = {'key': key, 'tables': tables, 'n': n, 'step': step, 'params': list(sel)}
         return loss
 
     def state_dict(self):
         # the per-parameter 'step' tensors torch.optim.Adam exposes are materialised lazily (host-side bookkeeping
         # uses a python int so that a training step does not touch 112 CPU tensors)
+        self._flush_fast()
         for st in self.state.values():
             if '_step' in st:
                 st['step'].fill_(float(st['_step']))
