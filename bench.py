@@ -234,16 +234,24 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         inputs = {"step": torch.tensor([float(i)]), "A_global": a, "B_global": b}
         if i % every == 0:
             inputs["A"] = A_host
-        nbytes = sum(v.numel() * v.element_size() for v in inputs.values())
-        inputs = {k: v.to(dev, non_blocking=True) for k, v in inputs.items()}   # train.py:54-55
+        nbytes = sum(v.numel() * v.element_size() for k, v in inputs.items() if k != "step")
+        inputs = {k: (v if k == "step" else v.to(dev, non_blocking=True)) for k, v in inputs.items()}   # splice_b200/train.py
         opt.zero_grad()
         losses = crit(model(inputs), inputs)
-        val = losses["loss"].item()                                                # train.py:67
+        if args.log_sync:
+            val = losses["loss"].item()                                            # ref train.py:67
+        else:
+            loss_log.push(losses["loss"])                                          # splice_b200/train.py: pinned async read
+            val = loss_log.latest()
         losses["loss"].backward()
         opt.step()
         return nbytes, val
 
+    from splice_b200.util.util import AsyncScalarLog
+    loss_log = AsyncScalarLog()
+
     def barrier():
+        loss_log.flush()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -320,7 +328,9 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                    "l2": "per-step working set (~0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
                    "generator": "native fp32 SIMT conv/BN/LReLU kernels (splice_gen_*)"},
         "e2e": {"value": world * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": 4,
-                "steps": k_e2e, "note": "train.py loop body: pinned host crops -> device each step, loss.item() each step"},
+                "steps": k_e2e, "note": "splice_b200/train.py loop body: pinned host crops -> device each step, loss read back to the host each step ("
+                        + ("loss.item(), as ref train.py:67" if args.log_sync else "non-blocking pinned copy, value consumed <= 2 steps later")
+                        + "); the step counter stays on the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_persistent_kernel", "achieved": achieved, "peak": peaks["tflops"],
@@ -347,6 +357,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=80)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--log-sync", action="store_true", help="e2e leg: read the loss with .item() every step (ref train.py:67)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -56,6 +56,96 @@ __device__ __forceinline__ void block_reduce_vec(float (&v)[NV], float* red) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm statistics without a second launch: every block that produced a (count, mean, M2) partial of a channel
+// group takes a ticket; the block that draws the last ticket merges the partials of that group (fixed order: the
+// result does not depend on which block happens to be last) and writes the per-channel constants. The ticket counters
+// live in the slot, start at zero and are reset by the finishing block, so captured graphs can be replayed.
+// -------------------------------------------------------------------------------------------------
+struct BnFin {
+    const float* gamma;
+    const float* beta;
+    float4* konst;       // (mean, invstd, a, b) per channel; nullptr = no statistics wanted
+    float2* bstat;       // (mean, unbiased variance) for the running-statistics update
+    int* counter;        // one ticket counter per channel group of this layer
+    float eps;
+};
+
+// Merge of the (count, mean, M2) partials [nparts][C][3] of channel c by one warp, in double precision and in a fixed
+// order: total count and mean first, then M2 = sum(M2_i + n_i (mean_i - mean)^2) (the pairwise update of Chan et al.
+// summed over all parts; no divisions inside the loops, partials fetched eight at a time so that the L2 loads overlap).
+// Lane 0 writes the constants.
+__device__ __forceinline__ void bn_merge_channel(const float* part, int nparts, int C, int c, const BnFin& f) {
+    const int lane = threadIdx.x & 31;
+    double n = 0.0, s1 = 0.0;
+    for (int i0 = lane; i0 < nparts; i0 += 32 * 8) {
+        float nb[8], mb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            nb[u] = 0.f; mb[u] = 0.f;
+            if (i < nparts) {
+                const float* p = part + ((size_t)i * C + c) * 3;
+                nb[u] = __ldcg(p); mb[u] = __ldcg(p + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { n += (double)nb[u]; s1 += (double)nb[u] * (double)mb[u]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    const double mean = s1 / n;
+    double M2 = 0.0;
+    for (int i0 = lane; i0 < nparts; i0 += 32 * 8) {
+        float nb[8], mb[8], Mb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            nb[u] = 0.f; mb[u] = 0.f; Mb[u] = 0.f;
+            if (i < nparts) {
+                const float* p = part + ((size_t)i * C + c) * 3;
+                nb[u] = __ldcg(p); mb[u] = __ldcg(p + 1); Mb[u] = __ldcg(p + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double d = (double)mb[u] - mean;
+            M2 += (double)Mb[u] + (double)nb[u] * d * d;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
+    if (lane == 0) {
+        const double var = M2 / n;
+        const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+        const float a = f.gamma[c] * invstd;
+        f.konst[c] = make_float4((float)mean, invstd, a, f.beta[c] - (float)mean * a);
+        if (f.bstat) f.bstat[c] = make_float2((float)mean, (float)(n > 1.0 ? M2 / (n - 1.0) : var));
+    }
+}
+
+// Called by ALL threads of a block after thread 0 has written the block's partials of channels [c0, c0 + nch).
+// `expected` = number of blocks contributing to this channel group. Uses one int of shared memory (s_flag).
+__device__ __forceinline__ void bn_finish_if_last(const float* part, int nparts, int C, int c0, int nch, int group, int expected,
+                                                  const BnFin& f, int* s_flag) {
+    if (threadIdx.x == 0) {
+        __threadfence();                                  // partials visible before the ticket
+        const int ticket = atomicAdd(f.counter + group, 1);
+        const int last = ticket == expected - 1;
+        if (last) f.counter[group] = 0;                   // self-reset for the next launch / graph replay
+        *s_flag = last;
+    }
+    __syncthreads();
+    if (*s_flag) {
+        __threadfence();
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int j = w; j < nch; j += nw)
+            if (c0 + j < C) bn_merge_channel(part, nparts, C, c0 + j, f);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // forward convolution (+ producer BN/LeakyReLU on load, + bias, + optional sigmoid, + output statistics)
 //   one thread per output pixel (linear over N*Ho*Wo), CO_T output channels per thread, optional split over the
@@ -68,11 +158,12 @@ template <int K, int S, int CO_T>
 __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, InTf tf,
                                                                 const float* __restrict__ Wt, const float* __restrict__ bias,
                                                                 int Cout, float* __restrict__ y, int Ho, int Wo, int out_sigmoid,
-                                                                float* __restrict__ stats_part, int splitK) {
+                                                                float* __restrict__ stats_part, int splitK, BnFin fin) {
     constexpr int CI_C = 8, KK = K * K, PAD = (K - 1) / 2;
     __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
     __shared__ float2 s_ab[CI_C];
     __shared__ float red[4 * CO_T];
+    __shared__ int s_flag;
     const int P = N * Ho * Wo;
     const int p = blockIdx.x * CONV_THREADS + threadIdx.x;
     const bool active = p < P;
@@ -191,50 +282,67 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
                     o[0] = cnt; o[1] = mean[co]; o[2] = m2[co];
                 }
         }
+        if (fin.konst) bn_finish_if_last(stats_part, gridDim.x, Cout, co0, CO_T, blockIdx.y, gridDim.x, fin, &s_flag);
     }
 }
 
-// split-K epilogue: y = bias + sum of partials, and the BatchNorm statistics / constants of the channel in one go
-// (one block per channel; only used by the low-resolution layers, N*H*W <= a few thousand)
-__global__ void __launch_bounds__(256) conv_finish_bn_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
-                                                             float* __restrict__ y, int N, int C, int HW,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                             float4* __restrict__ konst, float2* __restrict__ bstat) {
+// split-K epilogue: y = bias + sum of partials, per-block statistics of the result and (last block of a channel) the
+// BatchNorm constants. grid (ceil(N*HW / 1024), C): 256 threads x 4 pixels of one channel
+__global__ void __launch_bounds__(256) conv_finish_stats_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
+                                                                float* __restrict__ y, int N, int C, int HW,
+                                                                float* __restrict__ stats_part, BnFin fin) {
     __shared__ float red[8];
-    const int c = blockIdx.x, count = N * HW;
+    __shared__ int s_flag;
+    const int c = blockIdx.y, count = N * HW;
     const size_t total = (size_t)N * C * HW;
     const float b = bias[c];
+    float v[4];
+    bool ok[4];
     float a[1] = {0.f};
-    for (int e = threadIdx.x; e < count; e += 256) {
-        const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
-        float v = b;
-        for (int k = 0; k < splitK; ++k) v += part[(size_t)k * total + idx];
-        y[idx] = v;
-        a[0] += v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = blockIdx.x * 1024 + i * 256 + threadIdx.x;
+        ok[i] = e < count;
+        v[i] = 0.f;
+        if (ok[i]) {
+            const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
+            float acc = b;
+            int k = 0;
+            for (; k + 4 <= splitK; k += 4) {
+                const float p0 = part[(size_t)k * total + idx], p1 = part[(size_t)(k + 1) * total + idx];
+                const float p2 = part[(size_t)(k + 2) * total + idx], p3 = part[(size_t)(k + 3) * total + idx];
+                acc += p0; acc += p1; acc += p2; acc += p3;
+            }
+            for (; k < splitK; ++k) acc += part[(size_t)k * total + idx];
+            y[idx] = acc;
+            v[i] = acc;
+            a[0] += acc;
+        }
     }
     block_reduce_vec<1>(a, red);
-    const float mean = a[0] / count;
+    const int nb = min(1024, count - (int)blockIdx.x * 1024);
+    const float mean = a[0] / nb;
     a[0] = 0.f;
-    for (int e = threadIdx.x; e < count; e += 256) {   // each thread re-reads exactly what it wrote
-        const float d = y[((size_t)(e / HW) * C + c) * HW + (e % HW)] - mean;
-        a[0] += d * d;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float d = v[i] - mean;
+        a[0] += ok[i] ? d * d : 0.f;
     }
     block_reduce_vec<1>(a, red);
     if (threadIdx.x == 0) {
-        const float var = a[0] / count;
-        const float invstd = rsqrtf(var + eps);
-        const float g = gamma[c] * invstd;
-        konst[c] = make_float4(mean, invstd, g, beta[c] - mean * g);
-        if (bstat) bstat[c] = make_float2(mean, count > 1 ? a[0] / (count - 1) : var);
+        float* o = stats_part + ((size_t)blockIdx.x * C + c) * 3;
+        o[0] = (float)nb; o[1] = mean; o[2] = a[0];
     }
+    bn_finish_if_last(stats_part, gridDim.x, C, c, 1, c, gridDim.x, fin, &s_flag);
 }
 
 // concat( crop(lrelu(bn(s_raw))), crop(bilinear_x2(T(u_raw))) ) -> cat raw, + statistics per channel
 __global__ void __launch_bounds__(256) cat_build_kernel(const float* __restrict__ s_raw, int Cs, int Hs, int Ws, InTf tf_s,
                                                         int offy_s, int offx_s, const float* __restrict__ u_raw, int Cu, int Hu,
                                                         int Wu, InTf tf_u, int offy_u, int offx_u, float* __restrict__ cat, int H,
-                                                        int W, float* __restrict__ stats_part) {
+                                                        int W, float* __restrict__ stats_part, BnFin fin) {
     __shared__ float red[8];
+    __shared__ int s_flag;
     const int tiles_x = (W + TW - 1) / TW;
     const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
     const int c = blockIdx.y, n = blockIdx.z, C = Cs + Cu;
@@ -271,45 +379,7 @@ __global__ void __launch_bounds__(256) cat_build_kernel(const float* __restrict_
         float* o = stats_part + (pb * C + c) * 3;
         o[0] = cnt; o[1] = mean; o[2] = a[0];
     }
-}
-
-// merge the per-block (count, mean, M2) partials of one channel (one warp per channel, fixed order),
-// produce (mean, invstd, a, b) and the batch statistics (mean, unbiased variance) the running-statistics update needs
-__global__ void __launch_bounds__(32) bn_finalize_kernel(const float* __restrict__ part, int nparts, int C,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                         float4* __restrict__ konst, float2* __restrict__ bstat) {
-    const int c = blockIdx.x, lane = threadIdx.x;
-    double n = 0.0, mean = 0.0, M2 = 0.0;
-    for (int i = lane; i < nparts; i += 32) {
-        const float* p = part + ((size_t)i * C + c) * 3;
-        const double nb = p[0], mb = p[1], Mb = p[2];
-        if (nb > 0.0) {
-            const double nn = n + nb, delta = mb - mean;
-            mean += delta * nb / nn;
-            M2 += Mb + delta * delta * n * nb / nn;
-            n = nn;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
-                     Mb = __shfl_xor_sync(0xffffffffu, M2, o);
-        const double nn = n + nb;
-        if (nn > 0.0) {
-            // symmetric merge so that both partners end with identical values
-            const double delta = mb - mean;
-            const double new_mean = (n * mean + nb * mb) / nn;
-            M2 = M2 + Mb + delta * delta * n * nb / nn;
-            mean = new_mean;
-            n = nn;
-        }
-    }
-    if (lane == 0) {
-        const double var = M2 / n;
-        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float a = gamma[c] * invstd;
-        konst[c] = make_float4((float)mean, invstd, a, beta[c] - (float)mean * a);
-        if (bstat) bstat[c] = make_float2((float)mean, (float)(n > 1.0 ? M2 / (n - 1.0) : var));
-    }
+    bn_finish_if_last(stats_part, gridDim.x * gridDim.z, C, c, 1, c, gridDim.x * gridDim.z, fin, &s_flag);
 }
 
 // nn.BatchNorm2d's running statistics (momentum 0.1, unbiased variance, num_batches_tracked) from the batch statistics
@@ -696,6 +766,7 @@ struct BnOut {                 // where the BatchNorm constants / running statis
     const float *gamma, *beta;
     float4* konst;
     float2* bstat;
+    int* counter;              // ticket counters of this BatchNorm layer (GEN_COUNTERS_PER_BN ints)
 };
 
 static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin, int Win, InTf tf, const float* Wt,
@@ -708,7 +779,12 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
     dim3 grid(ceil_div(P, CONV_THREADS), ceil_div(Cout, ct), sk);
     float* dst = sk > 1 ? split_part : y;
     float* stats = (sk > 1 || !bn) ? nullptr : stats_part;
-#define CF(KK, SS, CT) conv_fwd_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, sigmoid, stats, sk)
+    const float eps = 1e-5f;
+    BnFin fin{nullptr, nullptr, nullptr, nullptr, nullptr, eps};
+    if (bn) fin = BnFin{bn->gamma, bn->beta, bn->konst, bn->bstat, bn->counter, eps};
+    BnFin fin_conv = fin;
+    if (sk > 1) fin_conv.konst = nullptr;   // the split-K epilogue kernel does the statistics
+#define CF(KK, SS, CT) conv_fwd_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, sigmoid, stats, sk, fin_conv)
 #define CF3(KK, SS) do { if (ct == 4) CF(KK, SS, 4); else if (ct == 8) CF(KK, SS, 8); else CF(KK, SS, 16); } while (0)
     if (K == 1 && S == 1) CF3(1, 1);
     else if (K == 3 && S == 1) CF3(3, 1);
@@ -717,15 +793,11 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
 #undef CF3
 #undef CF
     SPLICE_LAUNCH_CHECK();
-    if (!bn) return SPLICE_OK;
-    const float eps = 1e-5f;
-    if (sk > 1) {
-        conv_finish_bn_kernel<<<Cout, 256, 0, st>>>(split_part, sk, bias, y, N, Cout, Ho * Wo, bn->gamma, bn->beta, eps, bn->konst,
-                                                    bn->bstat);
-    } else {
-        bn_finalize_kernel<<<Cout, 32, 0, st>>>(stats_part, (int)grid.x, Cout, bn->gamma, bn->beta, eps, bn->konst, bn->bstat);
+    if (bn && sk > 1) {
+        dim3 fgrid(ceil_div(P, 1024), Cout);
+        conv_finish_stats_kernel<<<fgrid, 256, 0, st>>>(split_part, sk, bias, y, N, Cout, Ho * Wo, stats_part, fin);
+        SPLICE_LAUNCH_CHECK();
     }
-    SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
 
@@ -782,6 +854,7 @@ GenEngine::~GenEngine() {
     for (auto& s : slots_) {
         cudaFree(s.pool);
         cudaFree(s.scratch);
+        cudaFree(s.counters);
         if (s.side) cudaStreamDestroy(s.side);
         if (s.ev_fork) cudaEventDestroy(s.ev_fork);
         if (s.ev_join) cudaEventDestroy(s.ev_join);
@@ -793,6 +866,10 @@ int GenEngine::ensure_scratch(Slot& s, size_t bytes) {
         SPLICE_CHECK_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
         SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
         SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    }
+    if (!s.counters) {
+        SPLICE_CHECK_CUDA(cudaMalloc(&s.counters, (size_t)GEN_BN * GEN_COUNTERS_PER_BN * sizeof(int)));
+        SPLICE_CHECK_CUDA(cudaMemset(s.counters, 0, (size_t)GEN_BN * GEN_COUNTERS_PER_BN * sizeof(int)));
     }
     if (bytes <= s.scratch_bytes) return SPLICE_OK;
     SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
@@ -926,27 +1003,38 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
     const float eps = 1e-5f;
 
     auto bn_out = [&](const Bn& b, float4* k) {
-        return BnOut{p.param[b.pg], p.param[b.pb], k, s.bstat + (size_t)b.idx * BSTAT_STRIDE};
+        return BnOut{p.param[b.pg], p.param[b.pb], k, s.bstat + (size_t)b.idx * BSTAT_STRIDE,
+                     s.counters + (size_t)b.idx * GEN_COUNTERS_PER_BN};
+    };
+    auto conv_bn_on = [&](const Conv& c, const Bn& b, const float* in, int hin, int win, InTf tf, float* y, int ho, int wo,
+                          float4* k, float* stats_scratch, float* split_scratch, cudaStream_t cs) -> int {
+        const BnOut bo = bn_out(b, k);
+        return launch_conv_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, p.param[c.pw], p.param[c.pb], c.cout, y, ho, wo, 0, &bo,
+                               stats_scratch, split_scratch, cs);
     };
     auto conv_bn = [&](const Conv& c, const Bn& b, const float* in, int hin, int win, InTf tf, float* y, int ho, int wo,
-                       float4* k) -> int {
-        const BnOut bo = bn_out(b, k);
-        return launch_conv_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, p.param[c.pw], p.param[c.pb], c.cout, y, ho, wo, 0, &bo, part,
-                               split, st);
-    };
+                       float4* k) -> int { return conv_bn_on(c, b, in, hin, win, tf, y, ho, wo, k, part, split, st); };
 
-    // down path
+    // down path. The 1x1 skip convolutions only feed the concats of the up path: they run on the slot's side stream (a
+    // parallel branch of the captured graph) with their own scratch (the weight-gradient region, idle during a forward).
+    cudaStream_t ss = s.side;
+    float* part_skip = split + SPLIT_FLOATS;
+    float* split_skip = part_skip + (1u << 20);
     const float* in = s.x;
     InTf tf_in{nullptr, 0};
     for (int i = 0; i < GEN_SCALES; ++i) {
         const Scale& c = sc_[i];
         ScaleBuf& b = s.sb[i];
-        GRC(conv_bn(c.s, c.bs, in, b.h, b.w, tf_in, b.s_raw, b.h, b.w, b.k_s));
+        SPLICE_CHECK_CUDA(cudaEventRecord(s.ev_fork, st));
+        SPLICE_CHECK_CUDA(cudaStreamWaitEvent(ss, s.ev_fork, 0));
+        GRC(conv_bn_on(c.s, c.bs, in, b.h, b.w, tf_in, b.s_raw, b.h, b.w, b.k_s, part_skip, split_skip, ss));
         GRC(conv_bn(c.d1, c.bd1, in, b.h, b.w, tf_in, b.d1_raw, b.hd, b.wd, b.k_d1));
         GRC(conv_bn(c.d2, c.bd2, b.d1_raw, b.hd, b.wd, InTf{b.k_d1, 1}, b.d2_raw, b.hd, b.wd, b.k_d2));
         in = b.d2_raw;
         tf_in = InTf{b.k_d2, 1};
     }
+    SPLICE_CHECK_CUDA(cudaEventRecord(s.ev_join, ss));
+    SPLICE_CHECK_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
     // up path
     for (int i = GEN_SCALES - 1; i >= 0; --i) {
         const Scale& c = sc_[i];
@@ -959,12 +1047,10 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
         const int oys = (b.h - th) / 2, oxs = (b.w - tw) / 2, oyu = (2 * hu - th) / 2, oxu = (2 * wu - tw) / 2;
         const int C = 4 + c.cdeep;
         dim3 grid(ceil_div(th, TH) * ceil_div(tw, TW), C, N);
-        cat_build_kernel<<<grid, 256, 0, st>>>(b.s_raw, 4, b.h, b.w, InTf{b.k_s, 1}, oys, oxs, u, c.cdeep, hu, wu, tf_u, oyu, oxu,
-                                               b.cat, th, tw, part);
-        SPLICE_LAUNCH_CHECK();
         {
             const BnOut bo = bn_out(c.bcat, b.k_cat);
-            bn_finalize_kernel<<<C, 32, 0, st>>>(part, N * (int)grid.x, C, bo.gamma, bo.beta, eps, bo.konst, bo.bstat);
+            cat_build_kernel<<<grid, 256, 0, st>>>(b.s_raw, 4, b.h, b.w, InTf{b.k_s, 1}, oys, oxs, u, c.cdeep, hu, wu, tf_u, oyu, oxu,
+                                                   b.cat, th, tw, part, BnFin{bo.gamma, bo.beta, bo.konst, bo.bstat, bo.counter, eps});
             SPLICE_LAUNCH_CHECK();
         }
         GRC(conv_bn(c.c1, c.bc1, b.cat, th, tw, InTf{b.k_cat, 0}, b.c1_raw, th, tw, b.k_c1));

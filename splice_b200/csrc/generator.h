@@ -12,6 +12,7 @@ static constexpr int GEN_PARAMS = 112;     // netG.parameters() order (oracle/sp
 static constexpr int GEN_BN = 30;          // BatchNorm2d layers, module order
 static constexpr int GEN_SLOTS = 4;
 static constexpr int BSTAT_STRIDE = 160;   // >= the widest BatchNorm (132 channels)
+static constexpr int GEN_COUNTERS_PER_BN = 160;   // ticket counters per BatchNorm layer (one per channel / channel tile)
 
 struct GenPointers {
     float* param[GEN_PARAMS];
@@ -67,6 +68,7 @@ private:
         size_t stats_floats = 0;
         void* scratch = nullptr;   // partial-reduction scratch of this slot: [BN statistics | split-K sums | wgrad partials]
         size_t scratch_bytes = 0;
+        int* counters = nullptr;   // ticket counters of the in-kernel BatchNorm finalisation (zero between launches)
         cudaStream_t side = nullptr;            // weight-gradient branch of the backward pass (forked from / joined into
         cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the caller's stream; becomes a parallel branch under capture)
         ScaleBuf sb[GEN_SCALES];

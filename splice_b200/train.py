@@ -17,7 +17,7 @@ from tqdm import tqdm
 from .data.Dataset import SingleImageDataset
 from .models.model import Model
 from .util.losses import LossG
-from .util.util import get_optimizer, get_scheduler, save_result
+from .util.util import AsyncScalarLog, get_optimizer, get_scheduler, save_result
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -52,16 +52,26 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
                               n_epochs_decay=cfg['scheduler_n_epochs_decay'],
                               lr_decay_iters=cfg['scheduler_lr_decay_iters'])
 
+    # Two host-side departures from the reference loop, both value-preserving: the `step` scalar stays on the host
+    # (Model / LossG accept it either way; on the device every `step % n == 0` test is a stream sync, ref model.py:19,
+    # losses.py:35,39), and the progress line reads the loss through a non-blocking pinned copy instead of `.item()`
+    # (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most two steps old.
+    log = None if cfg.get('log_sync', False) or not torch.cuda.is_available() else AsyncScalarLog()
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
         for epoch in tepoch:
-            inputs = {k: v.to(device) for k, v in dataset[0].items()}
+            inputs = {k: (v if k == 'step' else v.to(device, non_blocking=True)) for k, v in dataset[0].items()}
             optimizer.zero_grad()
             outputs = model(inputs)
             losses = criterion(outputs, inputs)
             loss_G = losses['loss']
             lr = optimizer.param_groups[0]['lr']
             tepoch.set_description(f"Epoch {epoch}")
-            tepoch.set_postfix(loss=loss_G.item(), lr=lr)
+            if log is None:
+                loss_val = loss_G.item()
+            else:
+                log.push(loss_G)
+                loss_val = log.latest()
+            tepoch.set_postfix(loss=loss_val, lr=lr)
 
             if epoch % cfg['log_images_freq'] == 0:
                 with torch.no_grad():
@@ -73,6 +83,8 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
             loss_G.backward()
             optimizer.step()
             scheduler.step()
+    if log is not None:
+        log.flush()
     return model
 
 

@@ -37,6 +37,56 @@ def get_optimizer(cfg, params):
     return NotImplementedError('optimizer [%s] is not implemented', cfg['optimizer'])
 
 
+class AsyncScalarLog:
+    """Non-blocking stand-in for the per-step `loss_G.item()` of the progress line (ref train.py:67).
+
+    `.item()` drains the stream every step, which leaves the GPU idle while the host enqueues the backward pass. Here
+    the scalar is copied into a pinned ring buffer behind an event; `latest()` returns the newest value whose copy has
+    landed (at most `depth` steps old - `push` waits for the oldest copy before reusing its slot, so the host never
+    runs more than `depth` steps ahead). `flush()` drains everything (end of the loop)."""
+
+    def __init__(self, depth: int = 2):
+        self.depth = depth
+        self._host = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self._events = [torch.cuda.Event() for _ in range(depth)]
+        self._busy = [False] * depth
+        self._n = 0
+        self._newest_done = -1          # sequence number of the newest landed value
+        self._seq = [-1] * depth
+        self.value = float('nan')
+
+    def _poll(self, block_slot=None):
+        for slot in range(self.depth):
+            if not self._busy[slot]:
+                continue
+            if slot == block_slot:
+                self._events[slot].synchronize()
+            if slot == block_slot or self._events[slot].query():
+                self._busy[slot] = False
+                if self._seq[slot] > self._newest_done:
+                    self._newest_done = self._seq[slot]
+                    self.value = float(self._host[slot])
+
+    def push(self, t: torch.Tensor) -> None:
+        slot = self._n % self.depth
+        if self._busy[slot]:
+            self._poll(block_slot=slot)
+        self._host[slot:slot + 1].copy_(t.detach().reshape(1), non_blocking=True)
+        self._events[slot].record()
+        self._busy[slot], self._seq[slot] = True, self._n
+        self._n += 1
+
+    def latest(self) -> float:
+        self._poll()
+        return self.value
+
+    def flush(self) -> float:
+        for slot in range(self.depth):
+            if self._busy[slot]:
+                self._poll(block_slot=slot)
+        return self.value
+
+
 def save_result(image_t, dataroot):
     """Writes <dataroot>/out/output.png (ref util.py:55-59)."""
     from torchvision.transforms import ToPILImage

@@ -6,7 +6,7 @@ import pytest
 
 from tools import gpu_checks
 
-CASES = [n for n in gpu_checks.CHECKS if n != "gemm_tc_timing"]
+CASES = [n for n in gpu_checks.CHECKS if n not in ("gemm_tc_timing", "attention_timing")]
 
 
 @pytest.mark.gpu

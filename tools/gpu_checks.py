@@ -299,6 +299,47 @@ def attention_fwd_bwd():
     return out
 
 
+def attention_timing():
+    """us per launch of the attention kernels at the ViT-B/8 step shapes (S = 2 and 4 sequences of t = 785, 12 heads),
+    20 back-to-back launches between CUDA events. Run once per SPLICE_B200_ATTN mode to compare tcgen05 vs mma.sync."""
+    import os
+    import torch
+    from splice_b200 import _lib
+    from splice_b200._lib import check as ck, cur_stream, ptr
+
+    out = []
+    for (S, t, H) in ((2, 785, 12), (4, 785, 12), (2, 197, 6)):
+        D = 64 * H
+        qkv = (torch.randn(S * t, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+        o = torch.zeros(S * t, D, device="cuda", dtype=torch.bfloat16)
+        do = torch.randn(S * t, D, device="cuda").to(torch.bfloat16)
+        lse = torch.zeros(S, H, t, device="cuda")
+        delta = torch.zeros(S, H, t, device="cuda")
+        dqkv = torch.zeros(S * t, 3 * D, device="cuda", dtype=torch.bfloat16)
+
+        def timeit(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps * 1e3
+
+        f = timeit(lambda: ck(_lib.splice_attention_fwd(ptr(qkv), ptr(o), ptr(lse), S, t, D, H, cur_stream())))
+        b = timeit(lambda: ck(_lib.splice_attention_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dqkv), S, t, D, H, cur_stream())))
+        gf = 4.0 * S * t * t * D / 1e6
+        out.append({"mode": os.environ.get("SPLICE_B200_ATTN", "tc"), "S": S, "t": t, "H": H, "fwd_us": round(f, 2), "bwd_us": round(b, 2),
+                    "fwd_tflops": round(gf / f, 1), "bwd_tflops": round(2.5 * gf / b, 1), "ok": True})
+    return out
+
+
+CHECKS["attention_timing"] = attention_timing
+
+
 @check
 def preprocess_fwd_bwd():
     import torch
