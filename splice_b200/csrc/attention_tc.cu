@@ -181,46 +181,62 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict_
             const int kvalid = min(128, t - j * 128);
             mbar_wait(&bar[S_FULL], j & 1);
             tc_fence_after();
+            // Both passes stream the 128 columns through two register buffers: the tcgen05.ld of chunk c+1 is in flight
+            // while chunk c is processed; maxima / sums are kept in 4 independent accumulators (no 32-deep chains).
+            const int nch = (kvalid + 31) >> 5;    // 32-column chunks holding valid keys (warp-uniform)
+            uint32_t va[32], vb[32];
             // pass 1: row maximum
-            float mx = -INFINITY;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            tmem_ld_32x32(tS + lane_addr, va);
+            tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (c * 32 < kvalid) {   // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld_32x32(tS + c * 32 + lane_addr, v);
-                    tmem_ld_wait();
+                if (c < nch) {
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    if (c + 1 < nch) tmem_ld_32x32(tS + (c + 1) * 32 + lane_addr, nxt);
                     if (c * 32 + 32 <= kvalid) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+                        for (int e = 0; e < 32; ++e) mx4[e & 3] = fmaxf(mx4[e & 3], __uint_as_float(cur[e]));
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) mx = (c * 32 + e < kvalid) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+                        for (int e = 0; e < 32; ++e)
+                            mx4[e & 3] = (c * 32 + e < kvalid) ? fmaxf(mx4[e & 3], __uint_as_float(cur[e])) : mx4[e & 3];
                     }
+                    if (c + 1 < nch) tmem_ld_wait();
                 }
             }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             const float m_new = fmaxf(m, mx * scale_log2);
             const float corr = ex2_approx(m - m_new);     // first tile: 2^(-inf) = 0
-            if (j > 0) mbar_wait(&bar[P_FREE], (j - 1) & 1);   // P_{j-1} V_{j-1} has read the P tile
             // pass 2: P = 2^(S * scale - m_new) -> bf16 operand tile, row sum
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            tmem_ld_32x32(tS + lane_addr, va);
+            if (j > 0) mbar_wait(&bar[P_FREE], (j - 1) & 1);   // P_{j-1} V_{j-1} has read the P tile
+            tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (c * 32 < kvalid) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tS + c * 32 + lane_addr, v);
-                    tmem_ld_wait();
-                    float p[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float x = ex2_approx(fmaf(__uint_as_float(v[e]), scale_log2, -m_new));
-                        p[e] = (c * 32 + e < kvalid) ? x : 0.f;
-                        sum += p[e];
-                    }
+                if (c < nch) {
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    if (c + 1 < nch) tmem_ld_32x32(tS + (c + 1) * 32 + lane_addr, nxt);
                     uint8_t* blk = sP + (c >> 1) * T128;
+                    const bool full = c * 32 + 32 <= kvalid;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) st_tile_chunk(blk, r, (c & 1) * 4 + q, pack8(p + 8 * q));
+                    for (int q = 0; q < 4; ++q) {
+                        float p[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = ex2_approx(fmaf(__uint_as_float(cur[q * 8 + e]), scale_log2, -m_new));
+                            p[e] = (full || c * 32 + q * 8 + e < kvalid) ? x : 0.f;
+                            sum4[e & 3] += p[e];
+                        }
+                        st_tile_chunk(blk, r, (c & 1) * 4 + q, pack8(p));
+                    }
+                    if (c + 1 < nch) tmem_ld_wait();
                 }
             }
+            const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             l = fmaf(l, corr, sum);
             m = m_new;
             tc_fence_before();
@@ -376,22 +392,34 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gri
             mbar_wait(&bar[S_FULL], j & 1);
             tc_fence_after();
             if (j > 0) mbar_wait(&bar[DS_FREE], (j - 1) & 1);    // dS_{j-1} K_{j-1} has read the dS tile
+            {
+                const int nch = (((kvalid + 15) & ~15) + 31) >> 5;   // 32-column chunks the dQ MMA will read (warp-uniform)
+                uint32_t s0[32], d0[32], s1[32], d1[32];
+                tmem_ld_32x32(tS + lane_addr, s0);
+                tmem_ld_32x32(tdP + lane_addr, d0);
+                tmem_ld_wait();
+                if (nch > 1) {     // chunk 1 in flight while chunk 0 is processed
+                    tmem_ld_32x32(tS + 32 + lane_addr, s1);
+                    tmem_ld_32x32(tdP + 32 + lane_addr, d1);
+                }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c * 32 < ((kvalid + 15) & ~15)) {   // warp-uniform: chunks the dQ MMA will read
-                    uint32_t sv[32], dv[32];
-                    tmem_ld_32x32(tS + c * 32 + lane_addr, sv);
-                    tmem_ld_32x32(tdP + c * 32 + lane_addr, dv);
-                    tmem_ld_wait();
-                    float ds[32];
+                for (int c = 0; c < 2; ++c) {
+                    if (c < nch) {
+                        uint32_t (&sv)[32] = c ? s1 : s0;
+                        uint32_t (&dv)[32] = c ? d1 : d0;
+                        if (c == 1) tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float p = ex2_approx(fmaf(__uint_as_float(sv[e]), scale_log2, -lse_r));
-                        const float g = p * (__uint_as_float(dv[e]) - dl);
-                        ds[e] = (c * 32 + e < kvalid) ? g : 0.f;
+                        for (int qq = 0; qq < 4; ++qq) {
+                            float ds[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float p = ex2_approx(fmaf(__uint_as_float(sv[qq * 8 + e]), scale_log2, -lse_r));
+                                const float g = p * (__uint_as_float(dv[qq * 8 + e]) - dl);
+                                ds[e] = (c * 32 + qq * 8 + e < kvalid) ? g : 0.f;
+                            }
+                            st_tile_chunk(sdS, r, c * 4 + qq, pack8(ds));
+                        }
                     }
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) st_tile_chunk(sdS, r, c * 4 + qq, pack8(ds + 8 * qq));
                 }
             }
             tc_fence_before();
@@ -548,24 +576,39 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
             mbar_wait(&bar[S_FULL], i & 1);
             tc_fence_after();
             if (i > 0) mbar_wait(&bar[P_FREE], (i - 1) & 1);
+            {
+                const int nch = (((qvalid + 15) & ~15) + 31) >> 5;
+                uint32_t s0[32], d0[32], s1[32], d1[32];
+                tmem_ld_32x32(tSt + lane_addr, s0);
+                tmem_ld_32x32(tdPt + lane_addr, d0);
+                tmem_ld_wait();
+                if (nch > 1) {
+                    tmem_ld_32x32(tSt + 32 + lane_addr, s1);
+                    tmem_ld_32x32(tdPt + 32 + lane_addr, d1);
+                }
+                const float4* lse4 = reinterpret_cast<const float4*>(st_lse);
+                const float4* dl4 = reinterpret_cast<const float4*>(st_dl);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c * 32 < ((qvalid + 15) & ~15)) {
-                    uint32_t sv[32], dv[32];
-                    tmem_ld_32x32(tSt + c * 32 + lane_addr, sv);
-                    tmem_ld_32x32(tdPt + c * 32 + lane_addr, dv);
-                    tmem_ld_wait();
-                    float p[32], ds[32];
+                for (int c = 0; c < 2; ++c) {
+                    if (c < nch) {
+                        uint32_t (&sv)[32] = c ? s1 : s0;
+                        uint32_t (&dv)[32] = c ? d1 : d0;
+                        if (c == 1) tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), scale_log2, -st_lse[c * 32 + e]));
-                        p[e] = pe;
-                        ds[e] = pe * (__uint_as_float(dv[e]) - st_dl[c * 32 + e]);
-                    }
+                        for (int qq = 0; qq < 4; ++qq) {
+                            float ls[8], dl[8], p[8], ds[8];
+                            *reinterpret_cast<float4*>(ls) = lse4[c * 8 + qq * 2];
+                            *reinterpret_cast<float4*>(ls + 4) = lse4[c * 8 + qq * 2 + 1];
+                            *reinterpret_cast<float4*>(dl) = dl4[c * 8 + qq * 2];
+                            *reinterpret_cast<float4*>(dl + 4) = dl4[c * 8 + qq * 2 + 1];
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        st_tile_chunk(sPt, r, c * 4 + qq, pack8(p + 8 * qq));
-                        st_tile_chunk(sdSt, r, c * 4 + qq, pack8(ds + 8 * qq));
+                            for (int e = 0; e < 8; ++e) {
+                                p[e] = ex2_approx(fmaf(__uint_as_float(sv[qq * 8 + e]), scale_log2, -ls[e]));
+                                ds[e] = p[e] * (__uint_as_float(dv[qq * 8 + e]) - dl[e]);
+                            }
+                            st_tile_chunk(sPt, r, c * 4 + qq, pack8(p));
+                            st_tile_chunk(sdSt, r, c * 4 + qq, pack8(ds));
+                        }
                     }
                 }
             }

@@ -516,6 +516,97 @@ def vit_loss_backward_b8():
     return _vit_loss_backward_case("dino_vitb8", 224, 217)
 
 
+
+def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95):
+    """One full optimisation step (netG on every crop batch -> LossG -> backward) at the shapes of a BASELINE.json
+    config, against the oracle evaluated in fp32 on the same device: per-term losses, d loss / d generated images,
+    netG parameter gradients. Teacher-forced (same parameters, same inputs)."""
+    import numpy as np
+    import torch
+
+    dino_vit, R = _oracle_on_gpu()
+    from bench import make_cfg, synth_image
+    from splice_b200.models.model import Model
+    from splice_b200.util.losses import LossG
+
+    cfg = make_cfg(name)
+    cfg.update(dino_global_patch_size=vit_size, global_A_crops_n_crops=n_crops, global_B_crops_n_crops=n_crops)
+    vit = dino_vit.build(name).cuda()
+    vsd = {k: v.detach() for k, v in vit.state_dict().items()}
+    torch.manual_seed(0)
+    model = Model(cfg)
+    crit = LossG(cfg, state_dict=vsd)
+    A, B = synth_image(1000, side, 8).cuda(), synth_image(1001, side, 16).cuda()
+    rng = np.random.default_rng(3)
+
+    def crops(img):
+        s = int(round(rng.uniform(crop_lo * side, side)))     # one crop size per batch (ref transforms.py:22-26)
+        out = []
+        for _ in range(n_crops):
+            y, x = rng.integers(0, side - s + 1), rng.integers(0, side - s + 1)
+            out.append(img[:, y:y + s, x:x + s])
+        return torch.stack(out).contiguous()
+
+    inputs = {"step": torch.tensor([float(step)]), "A_global": crops(A), "B_global": crops(B), "A": A[None].contiguous()}
+    crit.update_lambda_config(1)      # past the cls warm-up: ssim + cls + identity active
+    for p in model.netG.parameters():
+        p.grad = None
+    outputs = model(inputs)
+    for v in outputs.values():
+        v.retain_grad()
+    losses = crit(outputs, inputs)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+
+    # oracle: same generated images as leaves (ViT part), and the generator re-evaluated with autograd (netG part)
+    sd = {k: v.detach().clone() for k, v in model.netG.state_dict().items()}
+    params = {k: sd[k].requires_grad_(True) for k, _ in model.netG.named_parameters()}
+    lam = R.active_lambdas(cfg, step, R.active_lambdas(cfg, 1, None))
+    outs_ref = {"x_global": R.generator_forward(sd, inputs["A_global"]), "y_global": R.generator_forward(sd, inputs["B_global"])}
+    if "x_entire" in outputs:
+        outs_ref["x_entire"] = R.generator_forward(sd, inputs["A"])
+    for v in outs_ref.values():
+        v.retain_grad()
+    ref = R.loss_g(vsd, cfg, lam, outs_ref, inputs)
+    ref["loss"].backward()
+    r = {"model": name, "side": side, "n_crops": n_crops, "vit_size": vit_size, "step": step,
+         "crop_sizes": [int(inputs["A_global"].shape[-1]), int(inputs["B_global"].shape[-1])]}
+    worst = 0.0
+    for k, v in ref.items():
+        e = abs(float(losses[k]) - float(v)) / max(abs(float(v)), 1e-12)
+        r[k] = float(losses[k]); r[k + "_ref"] = float(v)
+        worst = max(worst, e)
+    r["loss_rel"] = worst
+    r["pix_maxabs"] = max(_maxabs(outputs[k], outs_ref[k]) for k in outputs)
+    r["dout_rel"] = max(_rel(outputs[k].grad, outs_ref[k].grad) for k in outputs if outputs[k].grad is not None)
+    num = sum(float((p.grad - params[k].grad).double().pow(2).sum()) for k, p in model.netG.named_parameters())
+    den = sum(float(params[k].grad.double().pow(2).sum()) for k, _ in model.netG.named_parameters())
+    r["pgrad_rel"] = (num / max(den, 1e-300)) ** 0.5
+    # stated tolerances (bf16 tensor-core ViT vs fp32 oracle): losses 5e-3 rel, d loss / d image 2e-2 rel-L2, generated pixels
+    # 1e-4 abs, netG gradients 3e-2 rel-L2 over all parameters (they inherit the d loss / d image error)
+    r["ok"] = r["loss_rel"] < 5e-3 and r["dout_rel"] < 2e-2 and r["pix_maxabs"] < 1e-4 and r["pgrad_rel"] < 3e-2
+    return [r]
+
+
+@check
+def config3_step_448():
+    """BASELINE.json configs[2]: 448x448 pair, ViT-B/8 (crops 426-448 px, antialiased resize down to 224)."""
+    return _config_step_case("dino_vitb8", 448, 1, 224, step=2)
+
+
+@check
+def config3_step_448_entire():
+    """same, on a step that adds the entire-image terms (netG on the full 448x448 A)."""
+    return _config_step_case("dino_vitb8", 448, 1, 224, step=75)
+
+
+@check
+def config5_step_multicrop_448vit():
+    """BASELINE.json configs[4] at a bounded size: multi-crop batches (2 crops per batch, BatchNorm statistics over the
+    crops) of a 512 px pair with the ViT run at 448 px (t = 3137: the N^2 stress of the self-similarity / attention)."""
+    return _config_step_case("dino_vitb8", 512, 2, 448, step=2)
+
+
 # ------------------------------------------------------------------------------------------------
 # reference-facing classes: teacher-forced steps against the golden fixtures made from the reference itself
 # ------------------------------------------------------------------------------------------------
