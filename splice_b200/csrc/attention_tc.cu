@@ -271,7 +271,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict_
 }
 
 // =================================================================================================================
-// backward, part 1: dQ and delta = rowsum(dO * O). CTA = (128-query tile, head, sequence); key tiles of 64
+// backward, part 0: delta[s,h,q] = sum_d dO[q, h*64 + d] * O[q, h*64 + d]  (one warp per token row; the 8 lanes that hold
+// the eight 16-byte chunks of a head reduce by shuffle). Lets the dQ and the dK/dV kernels run side by side.
+// =================================================================================================================
+__global__ void __launch_bounds__(128) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                                         int S, int t, int D) {
+    pdl_sync();
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= S * t) return;
+    const int s = row / t, q = row - s * t, H = D / HD;
+    const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)row * D);
+    const uint4* pd = reinterpret_cast<const uint4*>(dout + (size_t)row * D);
+    for (int c0 = 0; c0 < D / 8; c0 += 32) {       // D / 8 chunks of 8 bf16; D is a multiple of 64 => whole heads per pass
+        const int c = c0 + lane;
+        float dl = 0.f;
+        if (c < D / 8) {
+            const uint4 a = po[c], b = pd[c];
+            float2 x, y;
+            x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
+            x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
+            x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
+            x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
+        }
+        dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+        if ((lane & 7) == 0 && c < D / 8) delta[((size_t)s * H + (c >> 3)) * t + q] = dl;
+    }
+}
+
+// =================================================================================================================
+// backward, part 1: dQ. CTA = (128-query tile, head, sequence); key tiles of 64
 // =================================================================================================================
 namespace bdq {
 enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, DS_READY = 6, DS_FREE = 7, DQ_FULL = 8, NBAR = 9 };
@@ -282,9 +312,8 @@ static constexpr uint32_t SMEM = OFF_BAR + 128;
 
 __global__ void __launch_bounds__(192, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
-                      const __grid_constant__ CUtensorMap tm_do128, const bf16* __restrict__ o, const bf16* __restrict__ dout,
-                      const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int t, int D, float scale,
-                      float scale_log2) {
+                      const __grid_constant__ CUtensorMap tm_do128, const float* __restrict__ lse,
+                      const float* __restrict__ delta, bf16* __restrict__ dqkv, int t, int D, float scale, float scale_log2) {
     using namespace bdq;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -369,22 +398,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gri
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         const int q = q0 + r;
         const bool qok = q < t;
-        // delta = rowsum(dO * O) (consumed here and by the dK/dV kernel), lse of this row
-        float dl = 0.f;
-        if (qok) {
-            const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)(row_base + q) * D + h * HD);
-            const uint4* pd = reinterpret_cast<const uint4*>(dout + (size_t)(row_base + q) * D + h * HD);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 a = po[c], b = pd[c];
-                float2 x, y;
-                x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
-                x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
-                x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
-                x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
-            }
-            delta[((size_t)s * H + h) * t + q] = dl;
-        }
+        const float dl = qok ? delta[((size_t)s * H + h) * t + q] : 0.f;
         const float lse_r = qok ? lse[((size_t)s * H + h) * t + q] : INFINITY;   // +inf => P = 0 for padded query rows
 
         for (int j = 0; j < n; ++j) {
@@ -698,13 +712,28 @@ int attention_bwd_tc(const bf16* qkv, const bf16* o, const bf16* dout, const flo
     if ((rc = make_tmap_bf16(&td128, dout, S * t, D, D, 128))) return rc;
     if ((rc = make_tmap_bf16(&td64, dout, S * t, D, D, 64))) return rc;
     const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
+    SPLICE_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(ceil_div(S * t, 4)), dim3(128), 0, stream, o, dout, delta, S, t, D));
+    SPLICE_LAUNCH_CHECK();
+    // dQ and dK/dV only share read-only inputs: the dK/dV kernel runs on a side stream (a parallel branch when the
+    // caller is capturing a graph); one CTA of each fits an SM, so each hides the other's tensor-core / exponential phases
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!side) {
+        SPLICE_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SPLICE_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     dim3 grid(ceil_div(t, 128), H, S);
-    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dq_tc_kernel, grid, dim3(192), align_slack(bdq::SMEM), stream, tq128, tq64, td128, o, dout,
-                                 lse, delta, dqkv, t, D, scale, scale_log2));
+    SPLICE_CHECK_CUDA(cudaEventRecord(ev_fork, stream));
+    SPLICE_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dkv_tc_kernel, grid, dim3(192), align_slack(bkv::SMEM), side, tq128, tq64, td64, lse,
+                                 (const float*)delta, dqkv, t, D, scale, scale_log2));
     SPLICE_LAUNCH_CHECK();
-    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dkv_tc_kernel, grid, dim3(192), align_slack(bkv::SMEM), stream, tq128, tq64, td64, lse, delta,
-                                 dqkv, t, D, scale, scale_log2));
+    SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dq_tc_kernel, grid, dim3(192), align_slack(bdq::SMEM), stream, tq128, tq64, td128, lse,
+                                 (const float*)delta, dqkv, t, D, scale, scale_log2));
     SPLICE_LAUNCH_CHECK();
+    SPLICE_CHECK_CUDA(cudaEventRecord(ev_join, side));
+    SPLICE_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     return SPLICE_OK;
 }
 

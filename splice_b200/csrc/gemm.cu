@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
                                     int N, int K, GemmEpilogue ep) {
     using L = GemmSmem<BN, STAGES>;
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static_assert(2 * BN <= 512, "two accumulator stages must fit the 512 TMEM columns");
+    constexpr uint32_t ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;   // power-of-two column offset
+    constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;                                                 // of the second accumulator
+    static_assert(BN <= 256, "two accumulator stages must fit the 512 TMEM columns");
     constexpr int CS = CM * CN;                       // cluster size
     constexpr int A_ROWS = BM / CN, B_ROWS = BN / CM;   // rows of the A / B tile this CTA loads (and multicasts)
     static_assert(A_ROWS % 8 == 0 && B_ROWS % 8 == 0, "operand slices must be whole 8-row swizzle atoms");
@@ -247,7 +248,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
                 const uint32_t as = lt & 1u;
                 mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + as * BN;
+                const uint32_t tacc = tmem_base + as * ACC_STRIDE;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -282,7 +283,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
                 const int col = n0 + c * 32;
                 if (c < CHUNKS && col < N && m0 < M) {  // warp-uniform (a padded tile of the super-tile stores nothing)
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+                    tmem_ld_32x32(tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
                     tmem_ld_wait();
                     if (row < M) {
                         float v[32];
@@ -547,6 +548,7 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
         // Measured on B200 (tools/gpu_checks.py gemm_tc_timing, ViT-B/8 shapes): the 128x256 tile wins whenever there are
         // enough tiles to occupy the 148 persistent CTAs (it halves the A re-reads through L2, which bound the 128-wide
         // tiles); the short-M backward GEMMs with N = 768 prefer 128x128; sub-128 widths only for narrow outputs.
+        // (128x96 tiles - 104 instead of 78 CTAs at M = 1570, N = 768 - measured no faster than 128x128: not selected.)
         if (N % 256 == 0 && (M >= 2048 || N >= 2048)) bn = 256;
         else if (N >= 128) bn = 128;
         else bn = 64;
@@ -555,6 +557,7 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
 #define SPLICE_GEMM_CASE(BN_, ST_, CM_, CN_) \
     if (bn == BN_ && cm == CM_ && cn == CN_) return launch_persistent<BN_, ST_, CM_, CN_>(A, lda, B, ldb, M, N, K, ep, stream)
     SPLICE_GEMM_CASE(64, 6, 1, 1);
+    SPLICE_GEMM_CASE(96, 6, 1, 1);
     SPLICE_GEMM_CASE(128, 5, 1, 1); SPLICE_GEMM_CASE(128, 5, 2, 1); SPLICE_GEMM_CASE(128, 5, 1, 2);
     SPLICE_GEMM_CASE(128, 5, 2, 2); SPLICE_GEMM_CASE(128, 5, 4, 1); SPLICE_GEMM_CASE(128, 5, 4, 2);
     SPLICE_GEMM_CASE(256, 4, 1, 1); SPLICE_GEMM_CASE(256, 4, 2, 1); SPLICE_GEMM_CASE(256, 4, 1, 2);

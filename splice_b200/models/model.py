@@ -19,10 +19,14 @@ class Model(torch.nn.Module):
         if torch.cuda.is_available():
             # "inputs are on the device" marker: lets LossG start the targets' ViT pass on a side stream without waiting
             # for the generator work enqueued below (absent marker = it waits for the whole stream; same results)
-            ready = torch.cuda.Event()
-            ready.record()
+            # (a caller that copies the inputs on its own stream attaches the event of that copy itself - train.py does -,
+            # which lets the next step's targets start while this stream is still busy with the previous backward)
+            ready = None
             for v in input.values():
-                if torch.is_tensor(v) and v.is_cuda:
+                if torch.is_tensor(v) and v.is_cuda and getattr(v, "_splice_ready", None) is None:
+                    if ready is None:
+                        ready = torch.cuda.Event()
+                        ready.record()
                     v._splice_ready = ready
         calls = []
         if cfg['lambda_global_cls'] + cfg['lambda_global_ssim'] > 0:

@@ -17,7 +17,7 @@ from tqdm import tqdm
 from .data.Dataset import SingleImageDataset
 from .models.model import Model
 from .util.losses import LossG
-from .util.util import AsyncScalarLog, get_optimizer, get_scheduler, save_result
+from .util.util import AsyncScalarLog, InputStager, get_optimizer, get_scheduler, save_result
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -52,14 +52,15 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
                               n_epochs_decay=cfg['scheduler_n_epochs_decay'],
                               lr_decay_iters=cfg['scheduler_lr_decay_iters'])
 
-    # Two host-side departures from the reference loop, both value-preserving: the `step` scalar stays on the host
-    # (Model / LossG accept it either way; on the device every `step % n == 0` test is a stream sync, ref model.py:19,
-    # losses.py:35,39), and the progress line reads the loss through a non-blocking pinned copy instead of `.item()`
-    # (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most two steps old.
+    # Host-side departures from the reference loop, all value-preserving: the inputs are copied on their own stream and
+    # the `step` scalar stays on the host (InputStager; on the device every `step % n == 0` test is a stream sync, ref
+    # model.py:19, losses.py:35,39), and the progress line reads the loss through a non-blocking pinned copy instead of
+    # `.item()` (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most two steps old.
     log = None if cfg.get('log_sync', False) or not torch.cuda.is_available() else AsyncScalarLog()
+    stage = InputStager(device) if torch.cuda.is_available() else (lambda b: b)
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
         for epoch in tepoch:
-            inputs = {k: (v if k == 'step' else v.to(device, non_blocking=True)) for k, v in dataset[0].items()}
+            inputs = stage(dataset[0])
             optimizer.zero_grad()
             outputs = model(inputs)
             losses = criterion(outputs, inputs)

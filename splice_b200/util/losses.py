@@ -84,6 +84,7 @@ class LossG(torch.nn.Module):
         self.global_transform = GlobalTransform(self.engine, cfg['dino_global_patch_size'])
         self.overlap_targets = True     # targets' ViT pass on a side stream, in the shadow of the generator forward
         self._side = None
+        self._targets_consumed = None   # event: the loss kernels of the last forward() have read the targets' features
         self.lambdas = dict(
             lambda_global_cls=cfg['lambda_global_cls'],
             lambda_global_ssim=0,
@@ -174,6 +175,12 @@ class LossG(torch.nn.Module):
                 else:
                     for e in {id(e): e for e in ready}.values():
                         side.wait_event(e)
+                    # ... and for the previous step's loss kernels, which read the targets' features this pass overwrites.
+                    # Nothing else ties it to the main stream: it may run under the previous step's backward passes.
+                    if self._targets_consumed is not None:
+                        side.wait_event(self._targets_consumed)
+                for s in tgts:
+                    s["batch"].record_stream(side)
                 ft = eng.forward([s["img"] for s in tgts], hw, n_grad=0, slot=slot + 1, use_graph=True, stream=side.cuda_stream)
                 fg = eng.forward([s["img"] for s in gens], hw, n_grad=n_grad, slot=slot, use_graph=True)
                 main.wait_stream(side)
@@ -210,6 +217,8 @@ class LossG(torch.nn.Module):
         for name, kind, lam, _, _ in plan:
             weights[TERM_ORDER.index(name)] = float(lam)
         weighted_total(terms, weights, total)
+        self._targets_consumed = torch.cuda.Event()
+        self._targets_consumed.record(main)
 
         # 4. dgrad-only backward per group -> d(total)/d(generated image), assembled per generated batch
         grads_by_batch: Dict[int, torch.Tensor] = {}

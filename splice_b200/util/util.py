@@ -37,6 +37,34 @@ def get_optimizer(cfg, params):
     return NotImplementedError('optimizer [%s] is not implemented', cfg['optimizer'])
 
 
+class InputStager:
+    """Host -> device staging of one step's inputs on a dedicated copy stream (ref train.py:54-55 moves them on the
+    compute stream, where the copy queues behind the previous step's backward pass).
+
+    The returned tensors carry the copy's event as `_splice_ready`; the compute stream waits for it, and LossG lets the
+    ViT pass over the step's *target* crops - which depends on nothing but these copies - start right away, i.e. under
+    the previous step's backward passes. The `step` scalar stays on the host (Model / LossG accept it either way)."""
+
+    def __init__(self, device=None):
+        self.device = torch.device('cuda') if device is None else device
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def __call__(self, batch: dict) -> dict:
+        main = torch.cuda.current_stream(self.device)
+        out = {}
+        with torch.cuda.stream(self.stream):
+            for k, v in batch.items():
+                out[k] = v if (k == 'step' or not torch.is_tensor(v)) else v.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        main.wait_event(ev)
+        for k, v in out.items():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(main)
+                v._splice_ready = ev
+        return out
+
+
 class AsyncScalarLog:
     """Non-blocking stand-in for the per-step `loss_G.item()` of the progress line (ref train.py:67).
 

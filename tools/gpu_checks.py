@@ -92,6 +92,8 @@ def gemm_tc_multi_k():
 @check
 def gemm_tc_multi_tile_edges():
     out = []
+    out.append(_gemm_case(1570, 768, 3072, 96))     # 128x96 tiles (N % 96 == 0)
+    out.append(_gemm_case(785, 192, 768, 96))
     for bn in (64, 128, 256):
         out.append(_gemm_case(785, 768, 768, bn))   # ragged M
         out.append(_gemm_case(3140, 192, 768, bn))  # N not a multiple of the wide tiles
@@ -199,7 +201,9 @@ def gemm_tc_timing():
         C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         row = {"M": M, "N": N, "K": K}
         gf = 2.0 * M * N * K / 1e6   # MFLOP -> TFLOP/s = gf / us
-        for bn in (64, 128, 256):
+        for bn in (64, 96, 128, 256):
+            if N % bn:
+                continue
             us = timeit(lambda: ops.gemm(A, B, out16=C, bn_hint=bn + 11000))
             row[f"persist_bn{bn}"] = round(gf / us, 1)
         for (cm, cn) in CLUSTER_SHAPES:
@@ -727,6 +731,55 @@ def lossg_overlap_targets():
         r["ok"] = sorted(la) == sorted(lb) and r["loss_maxabs"] == 0.0 and r["grad_maxabs"] == 0.0
         out.append(r)
     return out
+
+
+@check
+def pipelined_steps_match_serial():
+    """Eight optimisation steps enqueued back to back with no host sync (inputs staged on the copy stream, the targets'
+    ViT pass of step n+1 free to start under the backward passes of step n, loss read through the pinned ring) must
+    give bit-identical losses and parameters to the same steps run with every overlap switched off and a device sync
+    after each one: the overlaps only reorder independent work."""
+    import torch
+
+    dino_vit, _ = _oracle_on_gpu()
+    from bench import make_cfg, synth_image, crop_schedule
+    from splice_b200.models.model import Model
+    from splice_b200.util.losses import LossG
+    from splice_b200.util.util import InputStager, get_optimizer
+
+    cfg = make_cfg("dino_vits16")
+    vsd = {k: v.detach() for k, v in dino_vit.build("dino_vits16").state_dict().items()}
+    A, B = synth_image(1000, 128, 8), synth_image(1001, 128, 16)
+    sched = [(a.pin_memory(), b.pin_memory()) for a, b in crop_schedule(A, B, 8, seed=1)]
+    runs = {}
+    for mode in ("pipelined", "serial"):
+        torch.manual_seed(0)
+        model = Model(cfg)
+        crit = LossG(cfg, state_dict=vsd)
+        opt = get_optimizer(cfg, model.netG.parameters())
+        stage = InputStager()
+        if mode == "serial":
+            crit.overlap_targets = False
+            model.netG.concurrent = False
+        losses = []
+        for i in range(8):
+            a, b = sched[i]
+            batch = {"step": torch.tensor([float(i)]), "A_global": a, "B_global": b, "A": A[None].pin_memory()}
+            inputs = stage(batch) if mode == "pipelined" else {k: (v if k == "step" else v.cuda()) for k, v in batch.items()}
+            opt.zero_grad()
+            out = crit(model(inputs), inputs)
+            losses.append(out["loss"].detach().clone())
+            out["loss"].backward()
+            opt.step()
+            if mode == "serial":
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        runs[mode] = ([float(l) for l in losses], [p.detach().clone() for p in model.netG.parameters()])
+    la, lb = runs["pipelined"][0], runs["serial"][0]
+    pmax = max(_maxabs(x, y) for x, y in zip(runs["pipelined"][1], runs["serial"][1]))
+    r = {"losses": la, "loss_maxabs": max(abs(x - y) for x, y in zip(la, lb)), "param_maxabs": pmax}
+    r["ok"] = r["loss_maxabs"] == 0.0 and pmax == 0.0
+    return [r]
 
 
 @check
