@@ -282,8 +282,15 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             ms = tm.item()
         return ms, extra
 
-    # warm-up from step 0 (covers the cls-warmup step, an "entire" step and every crop shape), then the timed legs
+    # priming (set-up, like a compiler's first run): the engine runs a launch sequence eagerly the first time it sees a
+    # (slot, shape), captures it as a CUDA graph the second time and replays it afterwards - 2 passes over the crop
+    # schedule plus the step-0 / step-75 variants put every graph of the timed region in place, whatever W is.
     i0 = 0
+    n_prime = 2 * len(sched_dev) + 2 * every + 2
+    for i in range(n_prime):
+        step_resident(i)
+    i0 += n_prime
+    # W warm-up steps, then the timed legs
     for i in range(args.warmup):
         step_resident(i0 + i)
     i0 += args.warmup
@@ -296,9 +303,10 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     clocks = sampler.stop() if rank == 0 else {}
     i0 += args.steps
     k_e2e = max(10, min(args.steps, 200))
-    for i in range(3):
+    n_warm_e2e = max(3, len(sched_host) + 8)   # every crop shape once: the copy stream's allocator pool fills (cudaMalloc)
+    for i in range(n_warm_e2e):
         step_e2e(i0 + i)
-    i0 += 3
+    i0 += n_warm_e2e
     ms_e2e, h2d = timed(step_e2e, i0, k_e2e)
     i0 += k_e2e
 
@@ -334,10 +342,11 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, reference step schedule (every 75th step adds the "
                                "entire-image terms), crops 213-224 px", "pairs": world, "parallelism": f"{world} independent pair(s), 1/GPU",
                    "l2": "per-step working set (~0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
-                   "generator": "native fp32 SIMT conv/BN/LReLU kernels (splice_gen_*)"},
+                   "generator": "native fp32 SIMT conv/BN/LReLU kernels (splice_gen_*)",
+                   "priming_steps": n_prime},
         "e2e": {"value": world * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": 4,
                 "steps": k_e2e, "note": "splice_b200/train.py loop body: pinned host crops -> device each step, loss read back to the host each step ("
-                        + ("loss.item(), as ref train.py:67" if args.log_sync else "non-blocking pinned copy, value consumed <= 2 steps later")
+                        + ("loss.item(), as ref train.py:67" if args.log_sync else "non-blocking pinned copy, value consumed <= 8 steps later")
                         + "); the step counter stays on the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -362,7 +371,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=80)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--log-sync", action="store_true", help="e2e leg: read the loss with .item() every step (ref train.py:67)")

@@ -69,6 +69,7 @@ SPLICE_API int splice_layernorm_fwd(const void* x, const void* gamma, const void
 SPLICE_API int splice_layernorm_bwd(const void* dy, const void* x, const void* stats, const void* gamma, const void* g_in,
                                     void* g_out, void* g16, int M, int D, void* stream);
 /* o = softmax(q k^T / 8) v per (sequence, head); qkv bf16 [S*t, 3D]; o bf16 [S*t, D]; lse fp32 [S,H,t] (log2 domain).
+ * tcgen05 / TMEM / TMA kernels (csrc/attention_tc.cu); SPLICE_B200_ATTN=legacy selects the mma.sync cross-check kernels.
  * ref: DINO Attention.forward behind models/extractor.py:83; the probs tap is extractor.py:44-45,57-61 */
 SPLICE_API int splice_attention_fwd(const void* qkv, void* o, void* lse, int S, int t, int D, int H, void* stream);
 SPLICE_API int splice_attention_bwd(const void* qkv, const void* o, const void* dout, const void* lse, void* delta_scratch,

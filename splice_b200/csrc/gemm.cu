@@ -219,14 +219,38 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    pdl_sync();   // everything above overlapped the previous kernel's tail; operands / outputs are touched from here on
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail. The next kernel may be
+    // scheduled from here on (it waits for this grid to complete before touching memory); each role waits for the
+    // previous grid right before ITS first dependent global access - the producer only after it has put the first
+    // weight (B) tiles in flight when the caller declared B constant, the epilogue before its first load / store.
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;   // running k-block counter across tiles (ring position)
+            bool first = true;
             for (int st = cluster_id; st < num_super; st += num_clusters) {
                 const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                int kb0 = 0;
+                if (first) {
+                    first = false;
+                    const int npre = ep.b_const ? (num_kb < STAGES ? num_kb : STAGES) : 0;
+                    for (int kb = 0; kb < npre; ++kb) {    // fresh ring: every stage is free
+                        mbar_arrive_expect_tx(&full_bar[kb], L::STAGE_BYTES);
+                        uint8_t* dB = smemB + kb * L::B_BYTES + mi * (B_ROWS * BK * 2);
+                        if constexpr (CM > 1) tma_load_2d_mc(dB, &tmB, &full_bar[kb], kb * BK, n0 + mi * B_ROWS, mask_b);
+                        else tma_load_2d(dB, &tmB, &full_bar[kb], kb * BK, n0);
+                    }
+                    pdl_wait();
+                    for (int kb = 0; kb < npre; ++kb) {
+                        uint8_t* dA = smemA + kb * L::A_BYTES + ni * (A_ROWS * BK * 2);
+                        if constexpr (CN > 1) tma_load_2d_mc(dA, &tmA, &full_bar[kb], kb * BK, m0 + ni * A_ROWS, mask_a);
+                        else tma_load_2d(dA, &tmA, &full_bar[kb], kb * BK, m0);
+                    }
+                    it = npre;
+                    kb0 = npre;
+                }
+                for (int kb = kb0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1u);      // all peers' MMAs have read stage s
@@ -271,6 +295,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
         const int half = e >> 2;           // column half of the tile
         constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
         uint32_t lt = 0;
+        pdl_wait();
         for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
             const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
             const uint32_t as = lt & 1u;
@@ -461,6 +486,10 @@ static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int
         }
         max_clusters = n;
     }
+    static int prefetch_b = -1;   // SPLICE_B200_GEMM_PREFETCH=0: no weight tiles ahead of the dependent-launch wait (A/B aid)
+    if (prefetch_b < 0) { const char* v = getenv("SPLICE_B200_GEMM_PREFETCH"); prefetch_b = (v && v[0] == '0') ? 0 : 1; }
+    GemmEpilogue epl = ep;
+    if (!prefetch_b) epl.b_const = 0;
     CUtensorMap tmA, tmB;
     int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM / CN);
     if (rc) return rc;
@@ -487,7 +516,7 @@ static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    SPLICE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, ep));
+    SPLICE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, epl));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

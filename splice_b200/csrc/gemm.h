@@ -32,6 +32,9 @@ struct GemmEpilogue {
     // fp32 export of the column slice [slice_c0, slice_c1) (layer-11 keys for the loss kernels)
     float* slice32 = nullptr;
     int slice_c0 = 0, slice_c1 = 0, ldslice = 0;
+    // B is a constant (a weight matrix no kernel of the stream writes): its first tiles may be fetched before the
+    // programmatic-dependent-launch wait, i.e. while the previous kernel is still draining
+    int b_const = 0;
 };
 
 enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1, GEMM_IMPL_TCGEN05_TILE = 2 };

@@ -290,6 +290,7 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
     RC(write_cls_rows(s.x0[0], cls_, pos, S, t, D, stream));
     {
         GemmEpilogue ep;
+            ep.b_const = 1;
         ep.c32 = s.x0[0]; ep.ldc32 = D; ep.bias = pe_b_;
         ep.rows_per_seq = t - 1; ep.pos = pos; ep.ldpos = D;
         PROF(PROF_GEMM, GEMM_FLOPS(S * (t - 1), D, pp3), 0.0, gemm_bf16_tn(s.patches, pp3, pe_w_, pp3, S * (t - 1), D, pp3, ep, a.gemm_impl, 0, stream));
@@ -299,6 +300,7 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
         PROF(PROF_ROWWISE, 0.0, 6.0 * M * D, layernorm_fwd(s.x0[l], L.ln1_g, L.ln1_b, s.a16, s.st1[l], M, D, d_.ln_eps, stream));
         {
             GemmEpilogue ep;
+            ep.b_const = 1;
             ep.c16 = s.qkv[l]; ep.ldc16 = 3 * D; ep.bias = L.qkv_b;
             if (a.qkv32_all) { ep.c32 = a.qkv32_all + (size_t)l * M * 3 * D; ep.ldc32 = 3 * D; }
             if (l == depth - 1 && a.keys32) { ep.slice32 = a.keys32; ep.slice_c0 = D; ep.slice_c1 = 2 * D; ep.ldslice = D; }
@@ -307,17 +309,20 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
         PROF(PROF_ATTN_FWD, 4.0 * S * (double)t * t * D, 0.0, attention_fwd(s.qkv[l], s.o[l], s.lse[l], S, t, D, H, stream));
         {
             GemmEpilogue ep;
+            ep.b_const = 1;
             ep.c32 = s.x1[l]; ep.ldc32 = D; ep.bias = L.proj_b; ep.residual = s.x0[l]; ep.ldr = D;
             PROF(PROF_GEMM, GEMM_FLOPS(M, D, D), 0.0, gemm_bf16_tn(s.o[l], D, L.proj_w, D, M, D, D, ep, a.gemm_impl, 0, stream));
         }
         PROF(PROF_ROWWISE, 0.0, 6.0 * M * D, layernorm_fwd(s.x1[l], L.ln2_g, L.ln2_b, s.a16, s.st2[l], M, D, d_.ln_eps, stream));
         {
             GemmEpilogue ep;
+            ep.b_const = 1;
             ep.c16 = s.h16; ep.ldc16 = 4 * D; ep.bias = L.fc1_b; ep.act = GEMM_ACT_GELU; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
             PROF(PROF_GEMM, GEMM_FLOPS(M, 4 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.fc1_w, D, M, 4 * D, D, ep, a.gemm_impl, 0, stream));
         }
         {
             GemmEpilogue ep;
+            ep.b_const = 1;
             ep.c32 = s.x0[l + 1]; ep.ldc32 = D; ep.bias = L.fc2_b; ep.residual = s.x1[l]; ep.ldr = D;
             PROF(PROF_GEMM, GEMM_FLOPS(M, D, 4 * D), 0.0, gemm_bf16_tn(s.h16, 4 * D, L.fc2_w, 4 * D, M, D, 4 * D, ep, a.gemm_impl, 0, stream));
         }
@@ -377,17 +382,20 @@ int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t str
         if (have_g) {
             {   // d(gelu out) = g W2 ; d(pre) = . * gelu'(pre)
                 GemmEpilogue ep;
+            ep.b_const = 1;
                 ep.c16 = s.dh16; ep.ldc16 = 4 * D; ep.act = GEMM_ACT_GELU_GRAD; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
                 PROF(PROF_GEMM, GEMM_FLOPS(Mg, 4 * D, D), 0.0, gemm_bf16_tn(s.g16, D, L.fc2_wT, D, Mg, 4 * D, D, ep, a.gemm_impl, 0, stream));
             }
             {   // d(LN2 out) = d(pre) W1
                 GemmEpilogue ep;
+            ep.b_const = 1;
                 ep.c32 = s.da; ep.ldc32 = D;
                 PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, 4 * D), 0.0, gemm_bf16_tn(s.dh16, 4 * D, L.fc1_wT, 4 * D, Mg, D, 4 * D, ep, a.gemm_impl, 0, stream));
             }
             PROF(PROF_ROWWISE, 0.0, 18.0 * Mg * D, layernorm_bwd(s.da, s.x1[l], s.st2[l], L.ln2_g, s.g, s.g, s.g16, Mg, D, stream));
             {   // d(attn out) = g Wproj
                 GemmEpilogue ep;
+            ep.b_const = 1;
                 ep.c16 = s.do16; ep.ldc16 = D;
                 PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, D), 0.0, gemm_bf16_tn(s.g16, D, L.proj_wT, D, Mg, D, D, ep, a.gemm_impl, 0, stream));
             }
@@ -401,6 +409,7 @@ int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t str
         if (!have_g && !(l == depth - 1 && a.dkeys32)) continue;  // still all-zero
         {   // d(LN1 out) = d(qkv) Wqkv
             GemmEpilogue ep;
+            ep.b_const = 1;
             ep.c32 = s.da; ep.ldc32 = D;
             PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, 3 * D), 0.0, gemm_bf16_tn(s.dqkv16, 3 * D, L.qkv_wT, 3 * D, Mg, D, 3 * D, ep, a.gemm_impl, 0, stream));
         }
@@ -409,6 +418,7 @@ int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t str
     }
     {   // d(patch pixels) = g Wpe  (cls rows produce rows that the adjoint resampler never reads)
         GemmEpilogue ep;
+            ep.b_const = 1;
         ep.c32 = s.dpatch; ep.ldc32 = pp3;
         PROF(PROF_GEMM, GEMM_FLOPS(Mg, pp3, D), 0.0, gemm_bf16_tn(s.g16, D, pe_wT_, D, Mg, pp3, D, ep, a.gemm_impl, 0, stream));
     }

@@ -54,6 +54,8 @@ class NativeSkip(nn.Sequential):
 
     def __init__(self):
         super().__init__()
+        self._params_cache = None
+        self._bns_cache = None
         self._eng = None
         self._ptrs = None
         self._ptr_sig = None
@@ -68,16 +70,37 @@ class NativeSkip(nn.Sequential):
 
     # ---- pointer tables ----------------------------------------------------------------------------
     def _param_list(self) -> List[torch.nn.Parameter]:
-        ps = list(self.parameters())
-        if len(ps) != _lib.GEN_PARAMS:
-            raise RuntimeError(f"NativeSkip expects {_lib.GEN_PARAMS} parameter tensors, found {len(ps)}")
+        # cached: walking the module tree costs ~0.1 ms and this is asked for several times per step. The Parameter
+        # OBJECTS of a module tree are stable (load_state_dict / .to() / optimizers update them in place); the cache is
+        # dropped when a sub-module is added (add_module below).
+        ps = self._params_cache
+        if ps is None:
+            ps = list(self.parameters())
+            if len(ps) != _lib.GEN_PARAMS:
+                raise RuntimeError(f"NativeSkip expects {_lib.GEN_PARAMS} parameter tensors, found {len(ps)}")
+            self._params_cache = ps
         return ps
 
     def _bn_list(self) -> List[nn.BatchNorm2d]:
-        bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
-        if len(bns) != _lib.GEN_BN:
-            raise RuntimeError(f"NativeSkip expects {_lib.GEN_BN} BatchNorm2d layers, found {len(bns)}")
+        bns = self._bns_cache
+        if bns is None:
+            bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+            if len(bns) != _lib.GEN_BN:
+                raise RuntimeError(f"NativeSkip expects {_lib.GEN_BN} BatchNorm2d layers, found {len(bns)}")
+            self._bns_cache = bns
         return bns
+
+    def add_module(self, name, module):
+        self.__dict__['_params_cache'] = None
+        self.__dict__['_bns_cache'] = None
+        return super().add_module(name, module)
+
+    def _apply(self, fn, *a, **kw):
+        # .to() / .cuda() / .float(): tensors may be replaced
+        self.__dict__['_params_cache'] = None
+        self.__dict__['_bns_cache'] = None
+        self.__dict__['_ptr_sig'] = None
+        return super()._apply(fn, *a, **kw)
 
     def _engine(self):
         if self._eng is None:

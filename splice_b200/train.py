@@ -55,7 +55,7 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     # Host-side departures from the reference loop, all value-preserving: the inputs are copied on their own stream and
     # the `step` scalar stays on the host (InputStager; on the device every `step % n == 0` test is a stream sync, ref
     # model.py:19, losses.py:35,39), and the progress line reads the loss through a non-blocking pinned copy instead of
-    # `.item()` (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most two steps old.
+    # `.item()` (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most eight steps old.
     log = None if cfg.get('log_sync', False) or not torch.cuda.is_available() else AsyncScalarLog()
     stage = InputStager(device) if torch.cuda.is_available() else (lambda b: b)
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:

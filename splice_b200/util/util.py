@@ -43,25 +43,54 @@ class InputStager:
 
     The returned tensors carry the copy's event as `_splice_ready`; the compute stream waits for it, and LossG lets the
     ViT pass over the step's *target* crops - which depends on nothing but these copies - start right away, i.e. under
-    the previous step's backward passes. The `step` scalar stays on the host (Model / LossG accept it either way)."""
+    the previous step's backward passes. The `step` scalar stays on the host (Model / LossG accept it either way).
 
-    def __init__(self, device=None):
+    The device side is a ring of `depth` persistent buffers per input name (views of the right shape are handed out),
+    so a step allocates nothing; a buffer is overwritten only after the work that was enqueued between its hand-out and
+    the following call has completed (event on the compute stream), however far the host runs ahead."""
+
+    def __init__(self, device=None, depth: int = 12):
         self.device = torch.device('cuda') if device is None else device
         self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self._rings = {}        # input name -> [[buffer, event marking the end of its last use], ...]
+        self._handed = []       # slots handed out by the previous call
+        self._n = 0
 
     def __call__(self, batch: dict) -> dict:
         main = torch.cuda.current_stream(self.device)
-        out = {}
+        if self._handed:        # everything that reads the previous call's buffers has been enqueued by now
+            done = torch.cuda.Event()
+            done.record(main)
+            for slot in self._handed:
+                slot[1] = done
+            self._handed = []
+        out, staged = {}, []
         with torch.cuda.stream(self.stream):
             for k, v in batch.items():
-                out[k] = v if (k == 'step' or not torch.is_tensor(v)) else v.to(self.device, non_blocking=True)
+                if k == 'step' or not torch.is_tensor(v) or v.is_cuda:
+                    out[k] = v
+                    continue
+                ring = self._rings.setdefault(k, [[None, None] for _ in range(self.depth)])
+                slot = ring[self._n % self.depth]
+                n = v.numel()
+                if slot[0] is None or slot[0].numel() < n or slot[0].dtype != v.dtype:
+                    if slot[0] is not None:
+                        slot[0].record_stream(main)      # the outgoing buffer may still be read
+                    slot[0] = torch.empty(n + n // 8, dtype=v.dtype, device=self.device)
+                if slot[1] is not None:
+                    self.stream.wait_event(slot[1])
+                d = slot[0][:n].view(v.shape)
+                d.copy_(v, non_blocking=True)
+                out[k] = d
+                staged.append(d)
+                self._handed.append(slot)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         main.wait_event(ev)
-        for k, v in out.items():
-            if torch.is_tensor(v) and v.is_cuda:
-                v.record_stream(main)
-                v._splice_ready = ev
+        for d in staged:
+            d._splice_ready = ev
+        self._n += 1
         return out
 
 
@@ -71,9 +100,9 @@ class AsyncScalarLog:
     `.item()` drains the stream every step, which leaves the GPU idle while the host enqueues the backward pass. Here
     the scalar is copied into a pinned ring buffer behind an event; `latest()` returns the newest value whose copy has
     landed (at most `depth` steps old - `push` waits for the oldest copy before reusing its slot, so the host never
-    runs more than `depth` steps ahead). `flush()` drains everything (end of the loop)."""
+    runs more than `depth` steps ahead; a deep ring absorbs host-side jitter). `flush()` drains everything (end of the loop)."""
 
-    def __init__(self, depth: int = 2):
+    def __init__(self, depth: int = 8):
         self.depth = depth
         self._host = torch.empty(depth, dtype=torch.float32).pin_memory()
         self._events = [torch.cuda.Event() for _ in range(depth)]
