@@ -573,17 +573,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         const float* L = lse + ((size_t)s * H + h) * t;
         const float* Dl = delta + ((size_t)s * H + h) * t;
-        auto load_stats = [&](int i) {     // +inf lse => P = 0 for query columns beyond the sequence
+        // (lse | delta) of the 64 queries of a tile: fetched one tile ahead into a register and parked in shared memory at
+        // the start of the tile that uses them, so that the global-load latency never sits between two tiles
+        // (+inf lse => P = 0 for query columns beyond the sequence)
+        auto fetch_stats = [&](int i) -> float {
             const int qi = i * 64 + (tid & 63);
-            float v;
-            if (tid < 64) v = (qi < t) ? L[qi] : INFINITY;
-            else v = (qi < t) ? Dl[qi] : 0.f;
-            s_stat[(i & 1) * 128 + tid] = v;
+            if (tid < 64) return (qi < t) ? L[qi] : INFINITY;
+            return (qi < t) ? Dl[qi] : 0.f;
         };
-        load_stats(0);
+        float stat_next = fetch_stats(0);
         for (int i = 0; i < n; ++i) {
-            rows_barrier();                    // stats of tile i visible; everyone is past tile i-1's reads of the other stage
-            if (i + 1 < n) load_stats(i + 1);
+            s_stat[(i & 1) * 128 + tid] = stat_next;
+            rows_barrier();                    // stats of tile i visible; everyone is past tile i-2's reads of this stage
+            if (i + 1 < n) stat_next = fetch_stats(i + 1);
             const float* st_lse = s_stat + (i & 1) * 128;
             const float* st_dl = st_lse + 64;
             const int qvalid = min(64, t - i * 64);

@@ -322,13 +322,22 @@ def attention_timing():
         dqkv = torch.zeros(S * t, 3 * D, device="cuda", dtype=torch.bfloat16)
 
         def timeit(fn, reps=20):
+            # the launches are captured into a CUDA graph and replayed: a python / ctypes call costs more host time than
+            # these kernels take, so back-to-back eager launches would time the host
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
+            st = torch.cuda.Stream()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(g, stream=st):
+                    for _ in range(reps):
+                        fn()
+            g.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(reps):
-                fn()
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps * 1e3
