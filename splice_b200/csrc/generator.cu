@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
                                                                 const float* __restrict__ Wt, const float* __restrict__ bias,
                                                                 int Cout, float* __restrict__ y, int Ho, int Wo, int out_sigmoid,
                                                                 float* __restrict__ stats_part, int splitK, BnFin fin) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     constexpr int CI_C = 8, KK = K * K, PAD = (K - 1) / 2;
     __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
     __shared__ float2 s_ab[CI_C];
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) conv_finish_stats_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
                                                                 float* __restrict__ y, int N, int C, int HW,
                                                                 float* __restrict__ stats_part, BnFin fin) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     __shared__ float red[8];
     __shared__ int s_flag;
     const int c = blockIdx.y, count = N * HW;
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(256) cat_build_kernel(const float* __restrict_
                                                         int offy_s, int offx_s, const float* __restrict__ u_raw, int Cu, int Hu,
                                                         int Wu, InTf tf_u, int offy_u, int offx_u, float* __restrict__ cat, int H,
                                                         int W, float* __restrict__ stats_part, BnFin fin) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     __shared__ float red[8];
     __shared__ int s_flag;
     const int tiles_x = (W + TW - 1) / TW;
@@ -394,6 +397,7 @@ struct RunningTable {
     int C[GEN_BN];
 };
 __global__ void __launch_bounds__(160) update_running_kernel(RunningTable t, float momentum) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     const int l = blockIdx.x, c = threadIdx.x;
     if (c < t.C[l]) {
         const float2 b = t.bstat[l][c];
@@ -410,6 +414,7 @@ __global__ void __launch_bounds__(160) update_running_kernel(RunningTable t, flo
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ y,
                                                             const float4* __restrict__ konst, int lrelu, int C, int HW,
                                                             float* __restrict__ part) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     __shared__ float red[16];
     const int c = blockIdx.y, n = blockIdx.z;
     const float4 k = konst[c];
@@ -431,6 +436,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 // dgamma += sum dz*yhat, dbeta += sum dz, (m1, m2) = sums / count
 __global__ void __launch_bounds__(32) bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
                                                              float* dgamma, float* dbeta, float2* __restrict__ m, int accumulate) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     const int c = blockIdx.x, lane = threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < nparts; i += 32) {
@@ -452,6 +458,7 @@ __global__ void __launch_bounds__(32) bn_bwd_finalize_kernel(const float* __rest
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ y,
                                                            const float4* __restrict__ konst, const float2* __restrict__ m, int lrelu,
                                                            int C, int HW, size_t total) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const int c = (i / HW) % C;
         const float4 k = konst[c];
@@ -467,6 +474,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
 __global__ void __launch_bounds__(256) bn_bwd_small_kernel(float* __restrict__ dA, const float* __restrict__ y,
                                                            const float4* __restrict__ konst, int lrelu, int N, int C, int HW,
                                                            float* dgamma, float* dbeta, int accumulate) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     __shared__ float red[16];
     const int c = blockIdx.x, count = N * HW;
     const float4 k = konst[c];
@@ -496,6 +504,7 @@ __global__ void __launch_bounds__(256) bn_bwd_small_kernel(float* __restrict__ d
 // d(sigmoid output) -> d(pre-sigmoid) for the final 1x1 conv
 __global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                           float* __restrict__ dy, size_t total) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const float o = out[i];
         dy[i] = dout[i] * o * (1.f - o);
@@ -508,6 +517,7 @@ template <int K, int S, int CI_T>
 __global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo,
                                                                   const float* __restrict__ Wt, int Cin, float* __restrict__ dX,
                                                                   int Hin, int Win, int accumulate, int splitK) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     constexpr int CO_C = 8, KK = K * K, PAD = (K - 1) / 2;
     __shared__ __align__(16) float s_w[CO_C][KK][CI_T];
     const int P = N * Hin * Win;
@@ -578,6 +588,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* _
 // dst (=|+=) sum over the split partials
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splitK, size_t total,
                                                            float* __restrict__ dst, int accumulate) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         float v = accumulate ? dst[i] : 0.f;
         for (int k = 0; k < splitK; ++k) v += part[(size_t)k * total + i];
@@ -597,6 +608,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf tf,
                                                          const float* __restrict__ dy, int Cout, int Ho, int Wo, int N,
                                                          float* __restrict__ part) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     constexpr int CO_T = 16, CI_T = 8, PAD = (K - 1) / 2, KK = K * K;
     constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K, IWP = IW + 1;
     constexpr int SX = CI_T * IH * IWP;
@@ -684,6 +696,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
 // grad_w += sum over chunks, grad_b += sum over chunks (fixed order)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nchunks, size_t nW, int Cout,
                                                            float* __restrict__ gw, float* __restrict__ gb, int accumulate) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     const size_t i = blockIdx.x * (size_t)256 + threadIdx.x;
     const size_t tot = nW + Cout;
     if (i >= tot) return;
@@ -696,6 +709,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // adjoint of cat_build for the skip branch: d(s activated) = d(cat)[:, :Cs] placed at the crop offset, zero elsewhere
 __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const float* __restrict__ dcat, int C, int H, int W, int Cs, int Hs, int Ws, int offy,
                                                            int offx, float* __restrict__ dS) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     const size_t total = (size_t)gridDim.z * Cs * Hs * Ws;
     const int n = blockIdx.z;
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < (size_t)Cs * Hs * Ws; i += (size_t)gridDim.x * 256) {
@@ -710,6 +724,7 @@ __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const float* __restri
 // adjoint of the bilinear x2 up-sampling (+ crop): d(u activated)[n,cu,yu,xu] = sum over the <= 4x4 fine pixels that read it
 __global__ void __launch_bounds__(256) cat_bwd_up_kernel(const float* __restrict__ dcat, int C, int H, int W, int Cs, int Cu, int Hu, int Wu, int offy,
                                                          int offx, float* __restrict__ dU) {
+    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     const int n = blockIdx.z;
     for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < (size_t)Cu * Hu * Wu; i += (size_t)gridDim.x * 256) {
         const int cu = i / ((size_t)Hu * Wu), yu = (i / Wu) % Hu, xu = i % Wu;
@@ -784,7 +799,7 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
     if (bn) fin = BnFin{bn->gamma, bn->beta, bn->konst, bn->bstat, bn->counter, eps};
     BnFin fin_conv = fin;
     if (sk > 1) fin_conv.konst = nullptr;   // the split-K epilogue kernel does the statistics
-#define CF(KK, SS, CT) conv_fwd_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, sigmoid, stats, sk, fin_conv)
+#define CF(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(conv_fwd_kernel<KK, SS, CT>, grid, dim3(CONV_THREADS), 0, st, x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, sigmoid, stats, sk, fin_conv))
 #define CF3(KK, SS) do { if (ct == 4) CF(KK, SS, 4); else if (ct == 8) CF(KK, SS, 8); else CF(KK, SS, 16); } while (0)
     if (K == 1 && S == 1) CF3(1, 1);
     else if (K == 3 && S == 1) CF3(3, 1);
@@ -795,7 +810,7 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
     SPLICE_LAUNCH_CHECK();
     if (bn && sk > 1) {
         dim3 fgrid(ceil_div(P, 1024), Cout);
-        conv_finish_stats_kernel<<<fgrid, 256, 0, st>>>(split_part, sk, bias, y, N, Cout, Ho * Wo, stats_part, fin);
+        SPLICE_CHECK_CUDA(launch_pdl(conv_finish_stats_kernel, fgrid, dim3(256), 0, st, (const float*)split_part, sk, bias, y, N, Cout, Ho * Wo, stats_part, fin));
         SPLICE_LAUNCH_CHECK();
     }
     return SPLICE_OK;
@@ -809,7 +824,7 @@ static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int
     pick_tiling(P, Cin, Cout, total, &ct, &sk);
     dim3 grid(ceil_div(P, CONV_THREADS), ceil_div(Cin, ct), sk);
     float* dst = sk > 1 ? split_part : dX;
-#define DG(KK, SS, CT) conv_dgrad_kernel<KK, SS, CT><<<grid, CONV_THREADS, 0, st>>>(dy, N, Cout, Ho, Wo, Wt, Cin, dst, Hin, Win, accumulate, sk)
+#define DG(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(conv_dgrad_kernel<KK, SS, CT>, grid, dim3(CONV_THREADS), 0, st, dy, N, Cout, Ho, Wo, Wt, Cin, dst, Hin, Win, accumulate, sk))
 #define DG3(KK, SS) do { if (ct == 4) DG(KK, SS, 4); else if (ct == 8) DG(KK, SS, 8); else DG(KK, SS, 16); } while (0)
     if (K == 1 && S == 1) DG3(1, 1);
     else if (K == 3 && S == 1) DG3(3, 1);
@@ -820,7 +835,7 @@ static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int
     SPLICE_LAUNCH_CHECK();
     if (sk > 1) {
         const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        sum_partials_kernel<<<blocks, 256, 0, st>>>(split_part, sk, total, dX, accumulate);
+        SPLICE_CHECK_CUDA(launch_pdl(sum_partials_kernel, dim3(blocks), dim3(256), 0, st, (const float*)split_part, sk, total, dX, accumulate));
         SPLICE_LAUNCH_CHECK();
     }
     return SPLICE_OK;
@@ -989,7 +1004,7 @@ int GenEngine::update_running_stats(const GenPointers& p, int slot, cudaStream_t
         t.rmean[l] = p.running_mean[l]; t.rvar[l] = p.running_var[l]; t.nbt[l] = p.num_batches_tracked[l];
         t.C[l] = order[l]->c;
     }
-    update_running_kernel<<<GEN_BN, 160, 0, st>>>(t, 0.1f);
+    SPLICE_CHECK_CUDA(launch_pdl(update_running_kernel, dim3(GEN_BN), dim3(160), 0, st, t, 0.1f));
     SPLICE_LAUNCH_CHECK();
     s.stats_pending = false;
     return SPLICE_OK;
@@ -1049,8 +1064,8 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
         dim3 grid(ceil_div(th, TH) * ceil_div(tw, TW), C, N);
         {
             const BnOut bo = bn_out(c.bcat, b.k_cat);
-            cat_build_kernel<<<grid, 256, 0, st>>>(b.s_raw, 4, b.h, b.w, InTf{b.k_s, 1}, oys, oxs, u, c.cdeep, hu, wu, tf_u, oyu, oxu,
-                                                   b.cat, th, tw, part, BnFin{bo.gamma, bo.beta, bo.konst, bo.bstat, bo.counter, eps});
+            SPLICE_CHECK_CUDA(launch_pdl(cat_build_kernel, grid, dim3(256), 0, st, (const float*)b.s_raw, 4, b.h, b.w, InTf{b.k_s, 1}, oys, oxs, u, c.cdeep, hu,
+                                         wu, tf_u, oyu, oxu, b.cat, th, tw, part, BnFin{bo.gamma, bo.beta, bo.konst, bo.bstat, bo.counter, eps}));
             SPLICE_LAUNCH_CHECK();
         }
         GRC(conv_bn(c.c1, c.bc1, b.cat, th, tw, InTf{b.k_cat, 0}, b.c1_raw, th, tw, b.k_c1));
@@ -1091,18 +1106,18 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, bool accumulate, cud
     auto bn_bwd = [&](const Bn& b, float* dA, const float* y, const float4* k, int lrelu, int hh, int ww, float2* m) -> int {
         const int HW = hh * ww;
         if ((size_t)N * HW <= 8192) {
-            bn_bwd_small_kernel<<<b.c, 256, 0, st>>>(dA, y, k, lrelu, N, b.c, HW, p.grad[b.pg], p.grad[b.pb], acc);
+            SPLICE_CHECK_CUDA(launch_pdl(bn_bwd_small_kernel, dim3(b.c), dim3(256), 0, st, dA, y, k, lrelu, N, b.c, HW, p.grad[b.pg], p.grad[b.pb], acc));
             SPLICE_LAUNCH_CHECK();
             return SPLICE_OK;
         }
         dim3 grid(ceil_div(HW, 2048), b.c, N);
-        bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dA, y, k, lrelu, b.c, HW, part);
+        SPLICE_CHECK_CUDA(launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, st, (const float*)dA, y, k, lrelu, b.c, HW, part));
         SPLICE_LAUNCH_CHECK();
-        bn_bwd_finalize_kernel<<<b.c, 32, 0, st>>>(part, N * (int)grid.x, b.c, (double)N * HW, p.grad[b.pg], p.grad[b.pb], m, acc);
+        SPLICE_CHECK_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3(b.c), dim3(32), 0, st, (const float*)part, N * (int)grid.x, b.c, (double)N * HW, p.grad[b.pg], p.grad[b.pb], m, acc));
         SPLICE_LAUNCH_CHECK();
         const size_t total = (size_t)N * b.c * HW;
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dA, y, k, m, lrelu, b.c, HW, total);
+        SPLICE_CHECK_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(blocks), dim3(256), 0, st, dA, y, k, (const float2*)m, lrelu, b.c, HW, total));
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
@@ -1128,13 +1143,13 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, bool accumulate, cud
             attr = true;
         }
         if (c.k == 1 && c.stride == 1)
-            conv_wgrad_kernel<1, 1><<<grid, 256, wgrad_smem_floats<1, 1>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            SPLICE_CHECK_CUDA(launch_pdl(conv_wgrad_kernel<1, 1>, grid, dim3(256), wgrad_smem_floats<1, 1>() * 4, ws, in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart));
         else if (c.k == 3 && c.stride == 1)
-            conv_wgrad_kernel<3, 1><<<grid, 256, wgrad_smem_floats<3, 1>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            SPLICE_CHECK_CUDA(launch_pdl(conv_wgrad_kernel<3, 1>, grid, dim3(256), wgrad_smem_floats<3, 1>() * 4, ws, in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart));
         else
-            conv_wgrad_kernel<3, 2><<<grid, 256, wgrad_smem_floats<3, 2>() * 4, ws>>>(in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart);
+            SPLICE_CHECK_CUDA(launch_pdl(conv_wgrad_kernel<3, 2>, grid, dim3(256), wgrad_smem_floats<3, 2>() * 4, ws, in, c.cin, hin, win, tf, dy, c.cout, ho, wo, N, wpart));
         SPLICE_LAUNCH_CHECK();
-        wgrad_reduce_kernel<<<ceil_div((int)(nW + c.cout), 256), 256, 0, ws>>>(wpart, chunks, nW, c.cout, p.grad[c.pw], p.grad[c.pb], acc);
+        SPLICE_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(ceil_div((int)(nW + c.cout), 256)), dim3(256), 0, ws, (const float*)wpart, chunks, nW, c.cout, p.grad[c.pw], p.grad[c.pb], acc));
         SPLICE_LAUNCH_CHECK();
         return SPLICE_OK;
     };
@@ -1145,7 +1160,8 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, bool accumulate, cud
     // final 1x1 conv + sigmoid
     {
         const size_t total = (size_t)N * 3 * H * W;
-        sigmoid_bwd_kernel<<<(int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, st>>>(s.dout_copy, s.out, s.dfin, total);
+        SPLICE_CHECK_CUDA(launch_pdl(sigmoid_bwd_kernel, dim3((int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8)), dim3(256), 0, st,
+                                     (const float*)s.dout_copy, (const float*)s.out, s.dfin, total));
         SPLICE_LAUNCH_CHECK();
         GRC(wgrad(final_, s.sb[0].c2_raw, H, W, InTf{s.sb[0].k_c2, 1}, s.dfin, H, W));
         GRC(dgrad(final_, s.dfin, H, W, s.sb[0].dA_c2, H, W, 0));
@@ -1168,11 +1184,11 @@ int GenEngine::backward_body(const GenPointers& p, Slot& s, bool accumulate, cud
         const int oyu = (2 * hu - h) / 2, oxu = (2 * wu - w) / 2;
         {
             dim3 grid(min(ceil_div(4 * h * w, 256), 148 * 8), 1, N);
-            cat_bwd_skip_kernel<<<grid, 256, 0, st>>>(b.dcat, C, h, w, 4, h, w, 0, 0, b.dA_s);
+            SPLICE_CHECK_CUDA(launch_pdl(cat_bwd_skip_kernel, grid, dim3(256), 0, st, (const float*)b.dcat, C, h, w, 4, h, w, 0, 0, b.dA_s));
             SPLICE_LAUNCH_CHECK();
             float* dU = (i == GEN_SCALES - 1) ? b.dA_d2 : s.sb[i + 1].dA_c2;
             dim3 grid2(min(ceil_div(c.cdeep * hu * wu, 256), 148 * 8), 1, N);
-            cat_bwd_up_kernel<<<grid2, 256, 0, st>>>(b.dcat, C, h, w, 4, c.cdeep, hu, wu, oyu, oxu, dU);
+            SPLICE_CHECK_CUDA(launch_pdl(cat_bwd_up_kernel, grid2, dim3(256), 0, st, (const float*)b.dcat, C, h, w, 4, c.cdeep, hu, wu, oyu, oxu, dU));
             SPLICE_LAUNCH_CHECK();
         }
     }
