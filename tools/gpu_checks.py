@@ -216,6 +216,26 @@ def gemm_tc_timing():
         row["tile_bn128"] = round(gf / us, 1)
         us = timeit(lambda: torch.matmul(A, B.t()))
         row["cublas"] = round(gf / us, 1)
+        # the fused epilogue the ViT's proj / fc2 GEMMs use (bias + fp32 residual, fp32 out), replayed from a CUDA graph
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+        out32 = torch.empty(M, N, device="cuda")
+        fn = lambda: ops.gemm(A, B, out32=out32, bias=bias, residual=res)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(reps):
+                    fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record()
+        torch.cuda.synchronize()
+        row["bias_res_fp32_graph_us"] = round(e0.elapsed_time(e1) / reps * 1e3, 2)
         row["ok"] = True
         out.append(row)
     return out
