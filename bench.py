@@ -86,16 +86,21 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self._stop_evt.is_set():
                     break
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:  # noqa: BLE001 - nvidia-smi missing: report no clocks rather than fail the bench
             pass
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Summary of the samples taken in [t0, t1] (host clock): the sampler is started well before the timed region
+        (nvidia-smi's start-up enumerates every GPU of the box and perturbs running work) and only what it saw DURING
+        the timed region is reported."""
         self._stop_evt.set()
         if self.proc is not None:
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1 + 0.25:
+                continue
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -195,6 +200,8 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     model_name, side = "dino_vitb8", 224
     cfg = make_cfg(model_name)
@@ -282,6 +289,9 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             ms = tm.item()
         return ms, extra
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # priming (set-up, like a compiler's first run): the engine runs a launch sequence eagerly the first time it sees a
     # (slot, shape), captures it as a CUDA graph the second time and replays it afterwards - 2 passes over the crop
     # schedule plus the step-0 / step-75 variants put every graph of the timed region in place, whatever W is.
@@ -294,13 +304,12 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     for i in range(args.warmup):
         step_resident(i0 + i)
     i0 += args.warmup
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     _lib.splice_launch_count_reset()
+    t_begin = time.time()
     ms, _ = timed(step_resident, i0, args.steps)
+    t_end = time.time()
     launches = _lib.splice_launch_count()
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else {}
     i0 += args.steps
     k_e2e = max(10, min(args.steps, 200))
     n_warm_e2e = max(3, len(sched_host) + 8)   # every crop shape once: the copy stream's allocator pool fills (cudaMalloc)
@@ -332,6 +341,10 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
+    traffic = None     # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tfile = sorted((ROOT / "profiles").glob("gemm_traffic_*.json"))
+    if tfile:
+        traffic = json.loads(tfile[-1].read_text()).get("dram_bytes_per_launch")
     g = prof["gemm_tcgen05"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     it_s = world * args.steps / (ms * 1e-3)
@@ -351,7 +364,10 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_persistent_kernel", "achieved": achieved, "peak": peaks["tflops"],
-                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per launch, ncu --set full (cold caches), profiles/gemm_traffic_*.json; "
+                                     "operands per launch are 5-19 MB (bf16 A + W), outputs stay in L2",
+                     "peak_source": peaks["src"],
                      "launches_per_step": g["count"] / n_prof, "avg_launch_us": 1e3 * g["ms"] / max(g["count"], 1),
                      "algorithmic_gflop_per_launch": g["flops"] / max(g["count"], 1) / 1e9,
                      "loop_vit_tflops": VIT_GFLOP_PER_STEP * (it_s / world) / 1e3,
