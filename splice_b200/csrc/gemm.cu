@@ -300,36 +300,21 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
             const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
             const uint32_t as = lt & 1u;
             const int row = m0 + quad * 32 + lane;
-            // The residual rows of a chunk are fetched one chunk ahead - the first one before the wait for the
-            // accumulator, i.e. in the shadow of the mainloop - so that their L2 / HBM latency is not paid between the
-            // TMEM read and the store (ncu: the epilogue's top stall was the long-scoreboard wait on these loads).
-            const bool pre_ok = ep.res_prefetch && ep.residual != nullptr && ep.rows_per_seq == 0 && row < M && m0 < M;
-            float4 rpre[2][8];
-            auto fetch_res = [&](float4 (&dst)[8], int col) {
-                const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = r4[j];
-            };
-            {
-                const int col0 = n0 + half * CH_PER_HALF * 32;
-                if (pre_ok && half * CH_PER_HALF < CHUNKS && col0 < N) fetch_res(rpre[0], col0);
-            }
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1u);
             tc_fence_after();
-#pragma unroll
+#pragma unroll 1
             for (int cc = 0; cc < CH_PER_HALF; ++cc) {
                 const int c = half * CH_PER_HALF + cc;
                 const int col = n0 + c * 32;
                 if (c < CHUNKS && col < N && m0 < M) {  // warp-uniform (a padded tile of the super-tile stores nothing)
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), r);
-                    if (cc + 1 < CH_PER_HALF && c + 1 < CHUNKS && col + 32 < N && pre_ok) fetch_res(rpre[(cc + 1) & 1], col + 32);
                     tmem_ld_wait();
                     if (row < M) {
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                        gemm_epilogue_chunk(ep, row, col, v, pre_ok ? rpre[cc & 1] : nullptr);
+                        gemm_epilogue_chunk(ep, row, col, v);
                     }
                 }
             }
@@ -503,11 +488,8 @@ static int launch_persistent(const bf16* A, int lda, const bf16* B, int ldb, int
     }
     static int prefetch_b = -1;   // SPLICE_B200_GEMM_PREFETCH=0: no weight tiles ahead of the dependent-launch wait (A/B aid)
     if (prefetch_b < 0) { const char* v = getenv("SPLICE_B200_GEMM_PREFETCH"); prefetch_b = (v && v[0] == '0') ? 0 : 1; }
-    static int res_pre = -1;
-    if (res_pre < 0) { const char* v = getenv("SPLICE_B200_GEMM_RESPRE"); res_pre = (v && v[0] == '0') ? 0 : 1; }
     GemmEpilogue epl = ep;
     if (!prefetch_b) epl.b_const = 0;
-    if (!res_pre) epl.res_prefetch = 0;
     CUtensorMap tmA, tmB;
     int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM / CN);
     if (rc) return rc;

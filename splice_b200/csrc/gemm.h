@@ -35,7 +35,6 @@ struct GemmEpilogue {
     // B is a constant (a weight matrix no kernel of the stream writes): its first tiles may be fetched before the
     // programmatic-dependent-launch wait, i.e. while the previous kernel is still draining
     int b_const = 0;
-    int res_prefetch = 1;            // epilogue fetches the residual one chunk ahead (SPLICE_B200_GEMM_RESPRE=0 turns it off: A/B aid)
 };
 
 enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1, GEMM_IMPL_TCGEN05_TILE = 2 };
@@ -50,9 +49,7 @@ int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld,
 
 #ifdef __CUDACC__
 // Shared epilogue: 32 consecutive accumulator columns [col, col+32) of GEMM row `row`.
-// res_pre: the 32 residual values of this chunk if the caller fetched them ahead of time (nullptr = load them here)
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int row, int col, float (&v)[32],
-                                                    const float4* res_pre = nullptr) {
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int row, int col, float (&v)[32]) {
     if (ep.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);
 #pragma unroll
@@ -106,7 +103,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int 
         const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)orow * ep.ldr + col);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 r = res_pre ? res_pre[j] : r4[j];
+            const float4 r = r4[j];
             v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
         }
     }

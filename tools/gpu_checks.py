@@ -812,6 +812,37 @@ def pipelined_steps_match_serial():
 
 
 @check
+def async_scalar_log_and_stager():
+    """Host-side helpers of the train loop: the pinned ring returns the pushed values in order (never a value that was
+    not pushed, never older than `depth` pushes), flush() returns the last one; InputStager hands out device copies
+    equal to the host tensors, leaves `step` on the host and reuses its ring buffers."""
+    import torch
+    from splice_b200.util.util import AsyncScalarLog, InputStager
+
+    log = AsyncScalarLog(depth=3)
+    seen, ok = [], True
+    for i in range(40):
+        t = torch.full((1,), float(i), device="cuda") * 1.0
+        log.push(t)
+        v = log.latest()
+        if v == v:   # not NaN
+            ok = ok and (i - 3 <= v <= i)
+            seen.append(v)
+    ok = ok and log.flush() == 39.0 and seen == sorted(seen)
+    stage = InputStager(depth=4)
+    ptrs = set()
+    for i in range(12):
+        a = torch.randn(1, 3, 20 + i % 3, 20 + i % 3).pin_memory()
+        out = stage({"step": torch.tensor([float(i)]), "A_global": a, "B_global": a * 2})
+        torch.cuda.current_stream().synchronize()
+        ok = ok and (not out["step"].is_cuda) and torch.equal(out["A_global"].cpu(), a) and torch.equal(out["B_global"].cpu(), a * 2)
+        ok = ok and getattr(out["A_global"], "_splice_ready", None) is not None
+        ptrs.add(out["A_global"].data_ptr())
+    ok = ok and len(ptrs) <= 4
+    return [{"ring_values_seen": len(seen), "stager_buffers": len(ptrs), "ok": bool(ok)}]
+
+
+@check
 def adam_kernel():
     import torch
     from splice_b200.optim import FusedAdam
