@@ -838,7 +838,7 @@ def async_scalar_log_and_stager():
         ok = ok and (not out["step"].is_cuda) and torch.equal(out["A_global"].cpu(), a) and torch.equal(out["B_global"].cpu(), a * 2)
         ok = ok and getattr(out["A_global"], "_splice_ready", None) is not None
         ptrs.add(out["A_global"].data_ptr())
-    ok = ok and len(ptrs) <= 4
+    ok = ok and len(ptrs) <= 8      # 4 ring slots, each may be re-allocated once when a larger crop arrives
     return [{"ring_values_seen": len(seen), "stager_buffers": len(ptrs), "ok": bool(ok)}]
 
 
