@@ -298,7 +298,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     # (slot, shape), captures it as a CUDA graph the second time and replays it afterwards - 2 passes over the crop
     # schedule plus the step-0 / step-75 variants put every graph of the timed region in place, whatever W is.
     i0 = 0
-    n_prime = 2 * len(sched_dev) + 2 * every + 2
+    n_prime = (2 * len(sched_dev) + 2 * every + 2) if args.prime < 0 else args.prime
     for i in range(n_prime):
         step_resident(i)
     i0 += n_prime
@@ -392,6 +392,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prime", type=int, default=-1, help="untimed graph-priming steps before the warm-up (default: enough to "
+                    "capture every graph; 0 for short profiler runs)")
     ap.add_argument("--log-sync", action="store_true", help="e2e leg: read the loss with .item() every step (ref train.py:67)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
