@@ -15,6 +15,7 @@ import yaml
 from tqdm import tqdm
 
 from .data.Dataset import SingleImageDataset
+from .data.prefetch import PrefetchedSamples
 from .models.model import Model
 from .util.losses import LossG
 from .util.util import AsyncScalarLog, InputStager, get_optimizer, get_scheduler, save_result
@@ -56,11 +57,15 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     # the `step` scalar stays on the host (InputStager; on the device every `step % n == 0` test is a stream sync, ref
     # model.py:19, losses.py:35,39), and the progress line reads the loss through a non-blocking pinned copy instead of
     # `.item()` (ref train.py:67) unless cfg['log_sync'] is set - the value shown is then at most eight steps old.
+    # ... and the samples (PIL augmentation + crops, ref train.py:53) are drawn by a worker thread a few steps ahead, in
+    # the same order from the same RNG streams (cfg['prefetch'] = 0 draws them inline like the reference).
     log = None if cfg.get('log_sync', False) or not torch.cuda.is_available() else AsyncScalarLog()
     stage = InputStager(device) if torch.cuda.is_available() else (lambda b: b)
+    depth = int(cfg.get('prefetch', 4))
+    feed = PrefetchedSamples(dataset, cfg['n_epochs'], depth=depth) if depth > 0 else None
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
         for epoch in tepoch:
-            inputs = stage(dataset[0])
+            inputs = stage(feed.next() if feed is not None else dataset[0])
             optimizer.zero_grad()
             outputs = model(inputs)
             losses = criterion(outputs, inputs)
@@ -86,6 +91,8 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
             scheduler.step()
     if log is not None:
         log.flush()
+    if feed is not None:
+        feed.close()
     return model
 
 

@@ -158,3 +158,46 @@ def test_generator_slot_policy_over_the_reference_step_schedule():
                 tokens[live[name]] = None
     # steady state: the call site -> slot mapping is stable (few CUDA-graph keys)
     assert pick_keep_slot(tokens) == 0
+
+
+def test_prefetched_samples_reproduce_the_inline_stream(tmp_path):
+    """The worker-thread feed hands out exactly the samples the reference loop would draw inline:
+    same numpy / torch RNG consumption order, `step` snapshotted per sample, the every-75th-step 'A' entry in place."""
+    import random
+
+    import numpy as np
+    import yaml
+    from PIL import Image
+
+    from splice_b200.data.Dataset import SingleImageDataset
+    from splice_b200.data.prefetch import PrefetchedSamples
+
+    rng = np.random.default_rng(7)
+    for sub in ("A", "B"):
+        (tmp_path / sub).mkdir()
+        Image.fromarray(rng.integers(0, 256, (96, 96, 3), dtype=np.uint8)).save(tmp_path / sub / "im.png")
+    from pathlib import Path
+    cfg = yaml.safe_load(open(Path(__file__).resolve().parents[1] / "splice_b200" / "conf" / "default" / "config.yaml"))
+    cfg["dataroot"] = str(tmp_path)
+
+    def seed():
+        random.seed(3); np.random.seed(3); torch.manual_seed(3)
+
+    n = 80
+    seed()
+    ds = SingleImageDataset(cfg)
+    inline = []
+    for _ in range(n):
+        s = ds[0]
+        inline.append({k: v.clone() for k, v in s.items()})
+    seed()
+    feed = PrefetchedSamples(SingleImageDataset(cfg), n, depth=3, pin=False)
+    got = list(feed)
+    feed.close()
+    assert len(got) == n
+    for a, b in zip(inline, got):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert "A" in got[0] and "A" in got[75] and "A" not in got[1]
+    assert [float(g["step"]) for g in got] == [float(i) for i in range(n)]

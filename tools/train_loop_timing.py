@@ -1,0 +1,33 @@
+"""Wall-clock it/s of the complete drop-in loop `splice_b200.train.train_model` (dataset augmentation, input staging,
+progress line, PNG + callback every `log_images_freq` steps) on a synthetic 224 px pair with DINO ViT-B/8 (seeded random
+DINO-style weights): inline sampling like the reference vs the prefetching feed. Diagnostic; run on the B200 box."""
+import os, sys, tempfile, time
+from pathlib import Path
+import numpy as np
+import torch
+from PIL import Image
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+os.environ["SPLICE_B200_RANDOM_DINO"] = "1"
+from splice_b200.train import train_model
+
+root = Path(tempfile.mkdtemp())
+for sub, seed, grid in (("A", 1000, 8), ("B", 1001, 16)):
+    (root / sub).mkdir()
+    rng = np.random.default_rng(seed)
+    low = rng.integers(0, 256, (grid, grid, 3), dtype=np.uint8)
+    img = np.asarray(Image.fromarray(low).resize((224, 224), Image.BICUBIC)).astype(np.float64)
+    Image.fromarray(np.clip(img + rng.normal(0, 8, img.shape), 0, 255).astype(np.uint8)).save(root / sub / "im.png")
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+for label, ov in (("prefetch=4, async log (default)", {}), ("prefetch=0 (inline sampling)", {"prefetch": 0}),
+                  ("prefetch=0, log_sync (reference loop semantics)", {"prefetch": 0, "log_sync": True}),
+                  ("prefetch=4, image logging off", {"log_images_freq": 10 ** 9})):
+    ov = {"dino_model_name": "dino_vitb8", "n_epochs": n, "seed": 0, **ov}
+    train_model(str(root), overrides={**ov, "n_epochs": 160})          # graph capture for every crop shape
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    train_model(str(root), overrides=ov)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"RESULT {label}: {n / dt:.1f} it/s ({dt / n * 1e3:.2f} ms/it incl. model construction)", flush=True)
