@@ -18,7 +18,7 @@ from .data.Dataset import SingleImageDataset
 from .data.prefetch import PrefetchedSamples
 from .models.model import Model
 from .util.losses import LossG
-from .util.util import AsyncScalarLog, InputStager, get_optimizer, get_scheduler, save_result
+from .util.util import AsyncImageLog, AsyncScalarLog, InputStager, get_optimizer, get_scheduler, save_result
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -61,6 +61,10 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     # the same order from the same RNG streams (cfg['prefetch'] = 0 draws them inline like the reference).
     log = None if cfg.get('log_sync', False) or not torch.cuda.is_available() else AsyncScalarLog()
     stage = InputStager(device) if torch.cuda.is_available() else (lambda b: b)
+    # ... and so is the image-logging branch (ref train.py:70-76): the full-size input is uploaded once, the output image
+    # is read back through pinned memory and the PNG / callback are delivered by poll() a step or two later.
+    imglog = AsyncImageLog(cfg['dataroot'], callback) if log is not None else None
+    A_full = None
     depth = int(cfg.get('prefetch', 4))
     feed = PrefetchedSamples(dataset, cfg['n_epochs'], depth=depth) if depth > 0 else None
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
@@ -80,17 +84,28 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
             tepoch.set_postfix(loss=loss_val, lr=lr)
 
             if epoch % cfg['log_images_freq'] == 0:
-                with torch.no_grad():
-                    output = model.netG(dataset.get_A().to(device))
-                save_result(output[0], cfg['dataroot'])
-                if callback is not None:
-                    callback(output[0])
+                if imglog is None:
+                    with torch.no_grad():
+                        output = model.netG(dataset.get_A().to(device))
+                    save_result(output[0], cfg['dataroot'])
+                    if callback is not None:
+                        callback(output[0])
+                else:
+                    if A_full is None:
+                        A_full = dataset.get_A().to(device)     # deterministic (ToTensor of the structure image): upload once
+                    with torch.no_grad():
+                        output = model.netG(A_full)
+                    imglog.push(output[0])
+            if imglog is not None:
+                imglog.poll()
 
             loss_G.backward()
             optimizer.step()
             scheduler.step()
     if log is not None:
         log.flush()
+    if imglog is not None:
+        imglog.flush()
     if feed is not None:
         feed.close()
     return model

@@ -144,6 +144,41 @@ class AsyncScalarLog:
         return self.value
 
 
+class AsyncImageLog:
+    """Deferred `save_result(output[0], dataroot)` + `callback(output[0])` of the image-logging branch (ref train.py:70-76).
+
+    The reference reads the image back right away, which drains the whole stream (the host runs a step or two ahead of
+    the device) and then encodes the PNG while the GPU idles. Here the image is copied into pinned host memory behind an
+    event; `poll()` - called once per step - writes the PNG and fires the callback for every image whose copy has landed.
+    Same files, same callback arguments in the same order (the tensor handed over lives on the host), at most a few steps
+    late; `flush()` at the end of the loop delivers whatever is still pending."""
+
+    def __init__(self, dataroot, callback=None):
+        self.dataroot, self.callback = dataroot, callback
+        self._pending = []          # (event, pinned image), oldest first
+
+    def push(self, image_t: torch.Tensor) -> None:
+        host = torch.empty(image_t.shape, dtype=image_t.dtype).pin_memory()
+        host.copy_(image_t.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((ev, host))
+
+    def poll(self, block: bool = False) -> None:
+        while self._pending:
+            ev, host = self._pending[0]
+            if not block and not ev.query():
+                return
+            ev.synchronize()
+            self._pending.pop(0)
+            save_result(host, self.dataroot)
+            if self.callback is not None:
+                self.callback(host)
+
+    def flush(self) -> None:
+        self.poll(block=True)
+
+
 def save_result(image_t, dataroot):
     """Writes <dataroot>/out/output.png (ref util.py:55-59)."""
     from torchvision.transforms import ToPILImage
