@@ -550,7 +550,7 @@ def vit_loss_backward_b8():
 
 
 
-def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95):
+def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width=None):
     """One full optimisation step (netG on every crop batch -> LossG -> backward) at the shapes of a BASELINE.json
     config, against the oracle evaluated in fp32 on the same device: per-term losses, d loss / d generated images,
     netG parameter gradients. Teacher-forced (same parameters, same inputs)."""
@@ -569,14 +569,19 @@ def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95):
     torch.manual_seed(0)
     model = Model(cfg)
     crit = LossG(cfg, state_dict=vsd)
-    A, B = synth_image(1000, side, 8).cuda(), synth_image(1001, side, 16).cuda()
+    if width is None:
+        A, B = synth_image(1000, side, 8).cuda(), synth_image(1001, side, 16).cuda()
+    else:   # non-square pair (height `side`, width `width`): square crops, non-square "entire" image and ViT input
+        A = synth_image(1000, max(side, width), 8)[:, :side, :width].contiguous().cuda()
+        B = synth_image(1001, max(side, width), 16)[:, :side, :width].contiguous().cuda()
     rng = np.random.default_rng(3)
 
     def crops(img):
-        s = int(round(rng.uniform(crop_lo * side, side)))     # one crop size per batch (ref transforms.py:22-26)
+        h, w = img.shape[1], img.shape[2]
+        s = int(round(rng.uniform(crop_lo * h, h)))            # one crop size per batch (ref transforms.py:22-26)
         out = []
         for _ in range(n_crops):
-            y, x = rng.integers(0, side - s + 1), rng.integers(0, side - s + 1)
+            y, x = rng.integers(0, h - s + 1), rng.integers(0, w - s + 1)
             out.append(img[:, y:y + s, x:x + s])
         return torch.stack(out).contiguous()
 
@@ -631,6 +636,14 @@ def config3_step_448():
 def config3_step_448_entire():
     """same, on a step that adds the entire-image terms (netG on the full 448x448 A)."""
     return _config_step_case("dino_vitb8", 448, 1, 224, step=75)
+
+
+@check
+def nonsquare_entire_step():
+    """SURVEY §8f rank 3 (the regime of the shipped 1200x900 pairs, at a bounded size): a 300x400 pair on an
+    "entire image" step - netG on the non-square full image, ViT input 224x298 (bicubic pos-embed interpolation,
+    t = 1037) next to the square 224x224 crops in the same step."""
+    return _config_step_case("dino_vitb8", 300, 1, 224, step=75, width=400)
 
 
 @check
