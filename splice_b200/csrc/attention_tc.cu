@@ -21,6 +21,8 @@
 //   dQ         S = Q K^T, dP = dO V^T, dQ += dS K          B = K [key][dh] MN-major for the last one
 // The forward does not rescale an accumulator in TMEM: each key tile's P V product lands in its own TMEM buffer and
 // the row threads fold it into fp32 registers with the running-max correction (o = o * 2^(m_old - m_new) + P V).
+// The backward is three launches: delta = rowsum(dO * O) (row kernel), then the dQ kernel and the dK/dV kernel side by
+// side on two streams (they only share read-only inputs; one CTA of each fits an SM). No atomics: deterministic.
 #include "attention.h"
 #include "gemm.h"
 

@@ -104,7 +104,7 @@ class AsyncScalarLog:
 
     def __init__(self, depth: int = 8):
         self.depth = depth
-        self._host = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self._host = torch.empty(depth, dtype=torch.float32, pin_memory=True)
         self._events = [torch.cuda.Event() for _ in range(depth)]
         self._busy = [False] * depth
         self._n = 0
@@ -158,7 +158,7 @@ class AsyncImageLog:
         self._pending = []          # (event, pinned image), oldest first
 
     def push(self, image_t: torch.Tensor) -> None:
-        host = torch.empty(image_t.shape, dtype=image_t.dtype).pin_memory()
+        host = torch.empty(image_t.shape, dtype=image_t.dtype, pin_memory=True)
         host.copy_(image_t.detach(), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
