@@ -1,14 +1,16 @@
 """bench.py — optimisation-loop iterations/second per image pair (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                 # splice_b200 arm (N>1: under torchrun)
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # reference arm: CPU oracle port
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {1,2,3,5}]   # splice_b200 arm (N>1: under torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]        # reference arm: CPU oracle port
 
 A "step" is one iteration of the reference loop (train.py:53-80 without tqdm/PNG logging): netG on the
 structure and appearance crops, the DINO-ViT objective (key self-similarity + [CLS] + key identity, plus the
-"entire image" terms every 75th step), backward into netG, Adam. Workload at N=1: BASELINE.json configs[1]
-(224x224 pair, DINO ViT-B/8), synthetic pair per SURVEY.md §8d, seeded random DINO-style ViT weights (no
-network for checkpoints). With N GPUs every rank optimises its own pair (weak scaling, no data-path collective;
-one NCCL broadcast of the packed ViT weights at start-up).
+"entire image" terms every 75th step), backward into netG, Adam. Default workload (--config 2) = BASELINE.json
+configs[1] (224x224 pair, DINO ViT-B/8), the configuration the metric is quoted on; --config 3 / 5 / 1 time
+configs[2] (448 px pair), configs[4] (896 px pair, 4 crops per batch, ViT at 448 px: t = 3137) and configs[0]
+(128 px pair, ViT-S/16). Synthetic pair per SURVEY.md §8d, seeded random DINO-style ViT weights (no network for
+checkpoints). With N GPUs every rank optimises its own pair (weak scaling, no data-path collective; one NCCL
+broadcast of the packed ViT weights at start-up); `value` is then the aggregate over the N pairs.
 
 Prints ONE JSON line (rank 0).
 """
@@ -31,7 +33,40 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "opt-loop iters/sec per image pair (DINO ViT-B/8, 224px)"
 UNIT = "it/s"
-VIT_GFLOP_PER_STEP = 983.2  # 4 forward + 2 dgrad-only backward ViT-B/8 sequences at t = 785
+ENTIRE_EVERY = 75   # conf/default/config.yaml entire_A_every
+
+# --config N -> BASELINE.json configs[N-1] (numbering of SURVEY.md §8d); `sched` = distinct crop pairs cycled through
+WORKLOADS = {
+    1: {"tag": "configs[0]", "model": "dino_vits16", "side": 128, "n_crops": 1, "vit_size": 224, "sched": 32},
+    2: {"tag": "configs[1]", "model": "dino_vitb8", "side": 224, "n_crops": 1, "vit_size": 224, "sched": 32},
+    3: {"tag": "configs[2]", "model": "dino_vitb8", "side": 448, "n_crops": 1, "vit_size": 224, "sched": 32},
+    5: {"tag": "configs[4]", "model": "dino_vitb8", "side": 896, "n_crops": 4, "vit_size": 448, "sched": 6},
+}
+VIT_ARCH = {"dino_vits16": (16, 384), "dino_vitb8": (8, 768)}   # patch, D (depth 12)
+VIT_LABEL = {"dino_vits16": "ViT-S/16", "dino_vitb8": "ViT-B/8"}
+
+
+def vit_tokens(w: dict) -> int:
+    p, _ = VIT_ARCH[w["model"]]
+    return 1 + (w["vit_size"] // p) ** 2
+
+
+def vit_gflop_per_step(w: dict) -> float:
+    """Algorithmic ViT work of a steady-state step: per crop 4 distinct forwards + 2 dgrad-only
+    backward sequences; F(t) = 12(24tD^2 + 4t^2D) + 6(t-1)Dp^2, B(t) = 12(24tD^2 + 8t^2D) + 6(t-1)Dp^2."""
+    p, D = VIT_ARCH[w["model"]]
+    t = vit_tokens(w)
+    F = 12 * (24 * t * D * D + 4 * t * t * D) + 6 * (t - 1) * D * p * p
+    B = 12 * (24 * t * D * D + 8 * t * t * D) + 6 * (t - 1) * D * p * p
+    return w["n_crops"] * (4 * F + 2 * B) / 1e9
+
+
+def workload_string(w: dict) -> str:
+    """One description for BOTH arms (the driver compares the strings)."""
+    lo = int(round(0.95 * w["side"]))
+    return (f"{w['tag']}: {w['side']}x{w['side']} pair, DINO {VIT_LABEL[w['model']]}, "
+            f"{w['n_crops']} crop(s) of {lo}-{w['side']} px per batch, ViT input {w['vit_size']} px (t = {vit_tokens(w)}), reference step "
+            f"schedule: the timed steps start right after an 'entire image' step, every {ENTIRE_EVERY}th step adds the entire-image terms")
 
 
 def synth_image(seed: int, side: int, grid: int) -> torch.Tensor:
@@ -53,9 +88,9 @@ def make_cfg(model_name: str) -> dict:
     return cfg
 
 
-def crop_schedule(A: torch.Tensor, B: torch.Tensor, n: int, seed: int, min_cover: float = 0.95):
-    """n (A_global, B_global) crop pairs with the reference's size law: side ~ U[0.95 h, h] rounded
-    (data/transforms.py:22-23), random position; augmentation colour ops do not change shapes and are skipped."""
+def crop_schedule(A: torch.Tensor, B: torch.Tensor, n: int, seed: int, min_cover: float = 0.95, n_crops: int = 1):
+    """n (A_global, B_global) crop batches [n_crops,3,s,s] with the reference's size law: one side ~ U[0.95 h, h] rounded
+    per batch (data/transforms.py:22-26), random positions; augmentation colour ops do not change shapes and are skipped."""
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n):
@@ -63,14 +98,17 @@ def crop_schedule(A: torch.Tensor, B: torch.Tensor, n: int, seed: int, min_cover
         for img in (A, B):
             h = img.shape[1]
             s = int(round(rng.uniform(min_cover * h, h)))
-            y, x = rng.integers(0, h - s + 1), rng.integers(0, h - s + 1)
-            pair.append(img[None, :, y:y + s, x:x + s].contiguous())
+            crops = []
+            for _ in range(n_crops):
+                y, x = rng.integers(0, h - s + 1), rng.integers(0, h - s + 1)
+                crops.append(img[:, y:y + s, x:x + s])
+            pair.append(torch.stack(crops).contiguous())
         out.append(tuple(pair))
     return out
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons every 100 ms while the timed region runs (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -81,7 +119,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self._stop_evt.is_set():
@@ -121,64 +159,108 @@ def measured_peaks() -> dict:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
+# reference arm / CPU baseline / GPU reference: the oracle port (nothing of splice_b200 is imported here)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps(model_name: str, side: int, n_warm: int, n_steps: int, budget_s: float):
-    """Times full optimisation steps of the CPU restatement of the reference (oracle/, validated against the
-    unmodified reference by oracle/make_golden.py). Returns (steps timed, seconds per step, threads)."""
-    from oracle import dino_vit, splice_ref as R
+class OracleLoop:
+    """The reference loop (train.py:53-80) restated with oracle/ only: fp32 torch ops on `device`, the reference's
+    duplicated ViT forwards, autograd backward, Adam. With `vit_wgrad` the ViT weights require grad like the
+    reference's never-frozen hub module (148 weight gradients nobody reads are computed every step)."""
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = make_cfg(model_name)
-    vit = dino_vit.build(model_name)
-    vsd = {k: v.detach() for k, v in vit.state_dict().items()}
-    from splice_b200.models.networks import define_G
+    def __init__(self, w: dict, device: str, vit_wgrad: bool, seed: int = 0):
+        from oracle import dino_vit, splice_ref as R
 
-    torch.manual_seed(0)
-    net = define_G(cfg["init_type"], cfg["init_gain"])
-    params = {k: p.detach().clone().requires_grad_(True) for k, p in net.named_parameters()}
-    bufs = {k: v for k, v in net.state_dict().items() if k not in params}
-    m = {k: torch.zeros_like(p) for k, p in params.items()}
-    v = {k: torch.zeros_like(p) for k, p in params.items()}
-    A, B = synth_image(1000, side, 8), synth_image(1001, side, 16)
-    sched = crop_schedule(A, B, 8, seed=0)
-    lam = R.active_lambdas(cfg, 1, None)
+        self.R, self.w, self.dev = R, w, torch.device(device)
+        self.cfg = make_cfg(w["model"])
+        self.cfg.update(dino_global_patch_size=w["vit_size"], global_A_crops_n_crops=w["n_crops"], global_B_crops_n_crops=w["n_crops"])
+        vit = dino_vit.build(w["model"])
+        self.vsd = {k: v.detach().to(self.dev).requires_grad_(vit_wgrad) for k, v in vit.state_dict().items()}
+        self.params = {k: v.to(self.dev).requires_grad_(True) for k, v in R.generator_init_state(seed, self.cfg["init_gain"]).items()}
+        self.m = {k: torch.zeros_like(p) for k, p in self.params.items()}
+        self.v = {k: torch.zeros_like(p) for k, p in self.params.items()}
+        A, B = synth_image(1000, w["side"], 8), synth_image(1001, w["side"], 16)
+        self.A = A[None].to(self.dev)
+        self.sched = [(a.to(self.dev), b.to(self.dev)) for a, b in crop_schedule(A, B, min(w["sched"], 8), seed=0, n_crops=w["n_crops"])]
+        self.lam = R.active_lambdas(self.cfg, 1, None)
+        self.n = 0
 
-    def one(step):
-        a, b = sched[step % len(sched)]
-        sd = {**bufs, **params}
-        outs = {"x_global": R.generator_forward(sd, a), "y_global": R.generator_forward(sd, b)}
-        s_idx = 2 + step + (1 if (2 + step) % cfg["entire_A_every"] == 0 else 0)   # steady-state steps only
-        loss = R.loss_g(vsd, cfg, R.active_lambdas(cfg, s_idx, lam), outs, {"A_global": a, "B_global": b})["loss"]
-        grads = torch.autograd.grad(loss, list(params.values()))
+    def step(self, idx: int) -> float:
+        """Step number `idx` of the reference schedule (idx % 75 == 0 adds the entire-image terms)."""
+        R, cfg = self.R, self.cfg
+        a, b = self.sched[idx % len(self.sched)]
+        outs = {"x_global": R.generator_forward(self.params, a), "y_global": R.generator_forward(self.params, b)}
+        if idx % cfg["entire_A_every"] == 0:
+            outs["x_entire"] = R.generator_forward(self.params, self.A)
+        self.lam = R.active_lambdas(cfg, idx, self.lam)
+        loss = R.loss_g(self.vsd, cfg, self.lam, outs, {"A_global": a, "B_global": b, "A": self.A})["loss"]
+        for p in self.params.values():
+            p.grad = None
+        loss.backward()
+        self.n += 1
         with torch.no_grad():
-            for (k, p), g in zip(params.items(), grads):
-                R.adam_step(p, g, m[k], v[k], step + 1, cfg["lr"], cfg["optimizer_beta1"], cfg["optimizer_beta2"])
-        return float(loss)
+            for k, p in self.params.items():
+                R.adam_step(p, p.grad, self.m[k], self.v[k], self.n, cfg["lr"], cfg["optimizer_beta1"], cfg["optimizer_beta2"])
+        return float(loss.detach())
 
+
+def cpu_reference_steps(w: dict, n_warm: int, n_steps: int, budget_s: float):
+    """Times full optimisation steps of the CPU restatement of the reference (oracle/, validated against the
+    unmodified reference by oracle/make_golden.py) on all host cores. The timed steps follow the reference schedule
+    starting right after an "entire image" step (index 76, 77, ...). Returns (steps timed, seconds per step, threads)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    loop = OracleLoop(w, "cpu", vit_wgrad=False)   # conservative: skips the reference's never-read ViT weight gradients
+    first = ENTIRE_EVERY + 1
     t_w = time.perf_counter()
     for i in range(n_warm):
-        one(i)
+        loop.step(first - n_warm + i if first - n_warm + i > 1 else 2 + i)
     est = (time.perf_counter() - t_w) / max(n_warm, 1)
     n = n_steps if est <= 0 else max(1, min(n_steps, int(budget_s / max(est, 1e-3))))
     t0 = time.perf_counter()
     for i in range(n):
-        one(n_warm + i)
+        loop.step(first + i)
     dt = (time.perf_counter() - t0) / n
     return n, dt, torch.get_num_threads()
+
+
+def gpu_reference_steps(w: dict, dev: torch.device, n_warm: int = 3, n_steps: int = 20):
+    """The honest GPU bar (SURVEY.md:98): the reference's own loop semantics - duplicated forwards,
+    autograd incl. the unused ViT weight gradients, unfused ops - on stock PyTorch CUDA kernels on the same B200, fp32
+    with torch's default TF32 switches (matmul: off, cuDNN convs: on). Returns it/s, or None when the reference's
+    autograd graph cannot fit (configs[4]: 12 ViT graphs of ~17 GB of attention probabilities each are alive at once)."""
+    if w["n_crops"] * 3 * 12 * 12 * vit_tokens(w) ** 2 * 4 * 3 > 120e9:
+        return None
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True
+    try:
+        loop = OracleLoop(w, str(dev), vit_wgrad=True)
+        first = ENTIRE_EVERY + 1
+        for i in range(n_warm):
+            loop.step(2 + i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_steps):
+            loop.step(first + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return n_steps / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        del loop
+        torch.cuda.empty_cache()
 
 
 def run_reference(args, rank: int) -> None:
     if rank != 0:
         return
-    n, dt, threads = cpu_reference_steps("dino_vitb8", 224, n_warm=1, n_steps=args.steps, budget_s=150.0)
+    w = WORKLOADS[args.config]
+    n, dt, threads = cpu_reference_steps(w, n_warm=1, n_steps=args.steps, budget_s=150.0)
     val = 1.0 / dt
-    sample = (f"{n} full optimisation steps (1 warm-up) of the CPU oracle port of the reference loop at configs[1] shapes "
+    sample = (f"{n} full optimisation steps (1 warm-up) of the CPU oracle port of the reference loop at {w['tag']} shapes "
               f"(requested --steps {args.steps}; bounded to ~150 s)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic pair (SURVEY §8d), seeded random DINO-style ViT weights",
-            "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, steady-state steps", "steps_timed": n},
+            "config": {"workload": workload_string(w)}, "steps_timed": n,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -205,8 +287,10 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    model_name, side = "dino_vitb8", 224
+    w = WORKLOADS[args.config]
+    model_name, side = w["model"], w["side"]
     cfg = make_cfg(model_name)
+    cfg.update(dino_global_patch_size=w["vit_size"], global_A_crops_n_crops=w["n_crops"], global_B_crops_n_crops=w["n_crops"])
 
     # ViT weights: rank 0 materialises them, one NCCL broadcast of the packed buffer
     sd0 = random_dino_state_dict(model_name)
@@ -222,10 +306,11 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     opt = get_optimizer(cfg, model.netG.parameters())
 
     A, B = synth_image(1000 + 2 * rank, side, 8), synth_image(1001 + 2 * rank, side, 16)
-    sched_host = [(a.pin_memory(), b.pin_memory()) for a, b in crop_schedule(A, B, 32, seed=rank)]
+    sched_host = [(a.pin_memory(), b.pin_memory()) for a, b in crop_schedule(A, B, w["sched"], seed=rank, n_crops=w["n_crops"])]
     sched_dev = [(a.to(dev), b.to(dev)) for a, b in sched_host]
     A_host, A_dev = A[None].pin_memory(), A[None].to(dev)
     every = cfg["entire_A_every"]
+    assert every == ENTIRE_EVERY
 
     def step_resident(i: int):
         a, b = sched_dev[i % len(sched_dev)]
@@ -291,6 +376,13 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             ms = tm.item()
         return ms, extra
 
+    def align(i: int) -> int:
+        """Untimed steps up to the next index == 1 (mod 75): both arms time the same stretch of the step schedule."""
+        while i % every != 1:
+            step_resident(i)
+            i += 1
+        return i
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -305,12 +397,14 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     # ... then settle: a freshly leased box keeps getting faster for a while (image still paging in, clocks / host
     # ramping up - seen as 128 -> 178 it/s over the first minute). Untimed windows of `every` (= 75) steps - one
     # "entire image" step each - until four consecutive windows no longer improve on the best one by more than 1 % (at
-    # least 6, at most 50 windows, <= ~25 s); the W
+    # least 6, at most 50 windows, <= ~25 s). Its effect is reported (config.settle: first / best window it/s); the W
     # warm-up steps and the timed region follow unchanged.
-    n_settle, best, stale = 0, None, 0
+    n_settle, best, stale, first_win, t_last_win = 0, None, 0, None, time.time()
     if args.prime < 0:
-        for w in range(50):
+        t_settle = time.perf_counter()
+        for wdw in range(50):
             torch.cuda.synchronize()
+            t_last_win = time.time()
             t0 = time.perf_counter()
             for i in range(every):
                 step_resident(i0 + i)
@@ -318,28 +412,34 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             dt = time.perf_counter() - t0
             i0 += every
             n_settle += every
+            first_win = dt if first_win is None else first_win
             if best is None or dt < 0.99 * best:
                 best, stale = (dt if best is None else min(best, dt)), 0
             else:
                 best, stale = min(best, dt), stale + 1
-            if w >= 5 and stale >= 4:
+            if (wdw >= 5 and stale >= 4) or (wdw >= 1 and time.perf_counter() - t_settle > 25.0):
                 break
     # W warm-up steps, then the timed legs
     for i in range(args.warmup):
         step_resident(i0 + i)
-    i0 += args.warmup
+    i0 = align(i0 + args.warmup)
     _lib.splice_launch_count_reset()
     t_begin = time.time()
     ms, _ = timed(step_resident, i0, args.steps)
     t_end = time.time()
     launches = _lib.splice_launch_count()
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else {}
+    # clocks: samples from the last settle window (the same steady workload, directly before) through the end of the
+    # timed region - the timed region of a short run (20 steps = 0.1 s) is shorter than nvidia-smi's sampling period
+    clocks = sampler.stop(min(t_last_win, t_begin), t_end) if rank == 0 else {}
+    if clocks:
+        clocks["window_s"] = round(t_end - min(t_last_win, t_begin), 3)
+        clocks["timed_region_s"] = round(t_end - t_begin, 3)
     i0 += args.steps
     k_e2e = max(10, min(args.steps, 200))
     n_warm_e2e = max(3, len(sched_host) + 8)   # every crop shape once: the copy stream's allocator pool fills (cudaMalloc)
     for i in range(n_warm_e2e):
         step_e2e(i0 + i)
-    i0 += n_warm_e2e
+    i0 = align(i0 + n_warm_e2e)
     ms_e2e, h2d = timed(step_e2e, i0, k_e2e)
     i0 += k_e2e
 
@@ -350,7 +450,8 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     eng = crit.engine
     eng.profile_enable(True)
     crit.overlap_targets = False
-    n_prof = 20
+    n_prof = 20 if w["n_crops"] == 1 else 4
+    i0 = align(i0)
     for i in range(n_prof):
         _lib.check(_lib.splice_debug_spin(25e3, _lib.cur_stream()), "splice_debug_spin")
         step_resident(i0 + i)
@@ -367,20 +468,25 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     peaks = measured_peaks()
     traffic = None     # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
     tfile = sorted((ROOT / "profiles").glob("gemm_traffic_*.json"))
-    if tfile:
+    if tfile and args.config == 2:
         traffic = json.loads(tfile[-1].read_text()).get("dram_bytes_per_launch")
     g = prof["gemm_tcgen05"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     it_s = world * args.steps / (ms * 1e-3)
+    vit_gf = vit_gflop_per_step(w)
     line = {
         "metric": METRIC, "value": it_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic pair (SURVEY §8d), seeded random DINO-style ViT weights",
-        "config": {"workload": "configs[1]: 224x224 pair, DINO ViT-B/8, reference step schedule (every 75th step adds the "
-                               "entire-image terms), crops 213-224 px", "pairs": world, "parallelism": f"{world} independent pair(s), 1/GPU",
-                   "l2": "per-step working set (~0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
-                   "generator": "native fp32 SIMT conv/BN/LReLU kernels (splice_gen_*)",
-                   "priming_steps": n_prime + n_settle},
+        "config": {"workload": workload_string(w), "pairs": world, "parallelism": f"{world} independent pair(s), 1/GPU",
+                   "value_is": "it/s of the one pair" if world == 1 else f"aggregate over the {world} pairs (sum of per-pair it/s; every rank times the same K steps, max over ranks)",
+                   "l2": "per-step working set (>= 0.7 GB of saved ViT activations) exceeds the 126 MB L2; no explicit flush",
+                   "generator": "native fp32 kernels (splice_gen_*)",
+                   "priming_steps": n_prime + n_settle,
+                   "settle": {"windows": n_settle // every, "first_window_it_s": (every / first_win) if first_win else None,
+                              "best_window_it_s": (every / best) if best else None,
+                              "note": "untimed 75-step windows until they stop getting faster (fresh boxes speed up for a while); "
+                                      "--prime 0 skips priming and settling"}},
         "e2e": {"value": world * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": 4,
                 "steps": k_e2e, "note": "splice_b200/train.py loop body: pinned host crops -> device each step, loss read back to the host each step ("
                         + ("loss.item(), as ref train.py:67" if args.log_sync else "non-blocking pinned copy, value consumed <= 8 steps later")
@@ -394,14 +500,26 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                      "peak_source": peaks["src"],
                      "launches_per_step": g["count"] / n_prof, "avg_launch_us": 1e3 * g["ms"] / max(g["count"], 1),
                      "algorithmic_gflop_per_launch": g["flops"] / max(g["count"], 1) / 1e9,
-                     "loop_vit_tflops": VIT_GFLOP_PER_STEP * (it_s / world) / 1e3,
-                     "loop_frac_of_peak": VIT_GFLOP_PER_STEP * (it_s / world) / 1e3 / peaks["tflops"]},
+                     "loop_vit_gflop_per_step": vit_gf,
+                     "loop_vit_tflops": vit_gf * (it_s / world) / 1e3,
+                     "loop_frac_of_peak": vit_gf * (it_s / world) / 1e3 / peaks["tflops"]},
         "kernel_classes_ms_per_step": {k: v["ms"] / n_prof for k, v in prof.items()},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        n, dt, threads = cpu_reference_steps(model_name, side, n_warm=1, n_steps=3, budget_s=25.0)
+    if world == 1 and not args.no_gpu_reference:
+        # release the product's engine memory first? not needed: the reference loop needs < 20 GB at configs[0..2]
+        val = gpu_reference_steps(w, dev, n_warm=3, n_steps=20 if w["side"] <= 448 else 4)
+        line["gpu_reference"] = {"value": val, "unit": UNIT, "kind": "oracle port of the unmodified reference loop on stock PyTorch CUDA kernels, fp32 "
+                                 "(matmul TF32 off, cuDNN TF32 on: torch defaults), same GPU, same shapes and step schedule",
+                                 "steps": 20 if w["side"] <= 448 else 4,
+                                 "note": None if val is not None else "not runnable: the reference keeps 12 ViT autograd graphs (~17 GB of attention "
+                                         "probabilities each at t = 3137) alive at once, more than the 180 GB of one B200"}
+    if world == 1 and not args.no_cpu_baseline and w["n_crops"] == 1:
+        n, dt, threads = cpu_reference_steps(w, n_warm=1, n_steps=3, budget_s=25.0)
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n} full optimisation steps (after 1 warm-up) of the CPU oracle port at the same shapes"}
+    elif world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": "not timed: one step of the reference at this config is ~40 TFLOP of fp32 and ~200 GB of autograd state on the host"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -413,7 +531,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json configs[N-1]; 2 = the headline config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--prime", type=int, default=-1, help="untimed graph-priming steps before the warm-up (default: enough to "
                     "capture every graph; 0 for short profiler runs)")
     ap.add_argument("--log-sync", action="store_true", help="e2e leg: read the loss with .item() every step (ref train.py:67)")

@@ -145,17 +145,70 @@ def interpolate_pos_embed(pos_embed: torch.Tensor, patch: int, ntok: int, h: int
     return torch.cat([pos_embed[:, :1], grid.permute(0, 2, 3, 1).reshape(1, -1, dim)], dim=1)
 
 
-def build(name: str, seed: int = 1234) -> DinoViT:
+def build(name: str, seed: int = 1234, stats: str = "init") -> DinoViT:
     """Deterministic stand-in model; the global torch RNG state is saved and restored around construction
-    so that seeding of the caller's own stream (train.py:29-31) is not disturbed."""
+    so that seeding of the caller's own stream (train.py:29-31) is not disturbed.
+
+    stats="init": DINO's initialisation (near-uniform softmax, no outlier channels: the benign case).
+    stats="trained": the same model re-scaled to the activation statistics a *trained* DINO ViT shows, which is
+    what stresses a reduced-precision implementation (see `apply_trained_statistics`)."""
     patch, dim, heads = ARCH[name]
     state = torch.get_rng_state()
     try:
         torch.manual_seed(seed)
         model = DinoViT(patch, dim, heads)
+        if stats == "trained":
+            apply_trained_statistics(model, seed + 1)
+        elif stats != "init":
+            raise ValueError(stats)
     finally:
         torch.set_rng_state(state)
     return model
+
+
+@torch.no_grad()
+def apply_trained_statistics(model: DinoViT, seed: int = 1235, logit_gain: float = 3.5, n_outlier: int = 3,
+                             outlier_gain: float = 60.0) -> None:
+    """Re-scales a freshly initialised stand-in so that its activations look like a trained DINO ViT's (the real
+    weights cannot be fetched offline):
+      * peaky attention: the query / key rows of every qkv projection are scaled by `logit_gain` each, so the
+        pre-softmax logits have a standard deviation of a few units (low-entropy softmax rows; with the plain init
+        they are ~0.3 and every row is near-uniform);
+      * massive activations: `n_outlier` residual-stream channels receive a large constant through the fc2 bias of
+        block 1 (+-`outlier_gain`, i.e. 50-100x the typical channel) and larger fc2 rows in the later blocks - the
+        "few channels dominate the LayerNorm statistics" regime of trained ViTs; the LayerNorm gains of those
+        channels are small, as in trained models;
+      * every bias is non-zero and the LayerNorm gains are not 1.
+    Both sides of a parity test receive the resulting state_dict, so this changes the *stress*, not the contract."""
+    g = torch.Generator().manual_seed(seed)
+    dim = model.embed_dim
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    outl = torch.randperm(dim, generator=g)[:n_outlier]
+    sign = torch.where(torch.rand(n_outlier, generator=g) < 0.5, -1.0, 1.0)
+    model.patch_embed.proj.bias.add_(rn(dim, std=0.05))
+    for i, blk in enumerate(model.blocks):
+        w = blk.attn.qkv.weight
+        w[:2 * dim] *= logit_gain * (384.0 / dim) ** 0.5   # q and k rows; logit variance grows with dim at fixed init std
+        blk.attn.qkv.bias.copy_(rn(3 * dim, std=0.1))
+        blk.attn.proj.bias.copy_(rn(dim, std=0.05))
+        blk.mlp.fc1.bias.copy_(rn(4 * dim, std=0.1))
+        blk.mlp.fc2.bias.copy_(rn(dim, std=0.05))
+        # once the massive channels exist (from block 1's output on) they dominate each row's variance; trained
+        # models compensate with larger LayerNorm gains on the ordinary channels
+        comp = (1.0 + n_outlier * outlier_gain ** 2 / dim) ** 0.5 if i >= 2 else 1.0
+        for nrm in (blk.norm1, blk.norm2):
+            nrm.weight.copy_(comp * (1.0 + rn(dim, std=0.25)).abs().clamp_min(0.05))
+            nrm.bias.copy_(rn(dim, std=0.1))
+            nrm.weight[outl] = 0.05 + 0.05 * torch.rand(n_outlier, generator=g)
+        if i == 1:
+            blk.mlp.fc2.bias[outl] = sign * outlier_gain
+        if i >= 2:
+            blk.mlp.fc2.weight[outl] *= 8.0
+    model.norm.weight.copy_((1.0 + rn(dim, std=0.25)).abs().clamp_min(0.05))
+    model.norm.bias.copy_(rn(dim, std=0.1))
 
 
 def hub_load_standin(repo: str, name: str, *args, **kwargs) -> DinoViT:

@@ -284,6 +284,38 @@ def generator_param_keys() -> List[str]:
     return keys
 
 
+def generator_init_state(seed: int = 0, init_gain: float = 0.02) -> Dict[str, Tensor]:
+    """A freshly initialised netG state (parameters only; BatchNorm running buffers never influence outputs because
+    .eval() is never called) with the reference's init law - Xavier-normal(gain) conv weights, zero biases, BatchNorm
+    weight ~ N(1, gain), bias 0 (networks.py:24-47) - drawn from a private generator. NOT the reference's RNG stream
+    (that is pinned by tests/golden via the product's define_G); used where only the shapes/statistics matter
+    (bench.py's reference arm must not import the product package)."""
+    g = torch.Generator().manual_seed(seed)
+    cin = (3,) + CH_DOWN[:-1]
+    sd: Dict[str, Tensor] = {}
+
+    def conv(key, co, ci, k):
+        std = init_gain * math.sqrt(2.0 / (ci * k * k + co * k * k))
+        sd[key + ".weight"] = torch.randn(co, ci, k, k, generator=g) * std
+        sd[key + ".bias"] = torch.zeros(co)
+
+    def bn(key, c):
+        sd[key + ".weight"] = 1.0 + init_gain * torch.randn(c, generator=g)
+        sd[key + ".bias"] = torch.zeros(c)
+
+    for i in range(N_SCALES):
+        p = g_prefix(i)
+        deep = CH_DOWN[i] if i == N_SCALES - 1 else CH_UP[i + 1]
+        conv(p + "1.0.1.0", CH_SKIP, cin[i], 1); bn(p + "1.0.2", CH_SKIP)
+        conv(p + "1.1.1.0", CH_DOWN[i], cin[i], 3); bn(p + "1.1.2", CH_DOWN[i])
+        conv(p + "1.1.4.0", CH_DOWN[i], CH_DOWN[i], 3); bn(p + "1.1.5", CH_DOWN[i])
+        bn(p + "2", CH_SKIP + deep)
+        conv(p + "3.0", CH_UP[i], CH_SKIP + deep, 3); bn(p + "4", CH_UP[i])
+        conv(p + "6.0", CH_UP[i], CH_UP[i], 1); bn(p + "7", CH_UP[i])
+    conv("9.0", 3, CH_UP[0], 1)
+    return {k: sd[k] for k in generator_param_keys()}
+
+
 # ------------------------------------------------------------------------------------------------
 # Adam — util/util.py:28-32 -> torch.optim.Adam (lr 2e-3, betas (0, 0.99), eps 1e-8, no weight decay)
 # ------------------------------------------------------------------------------------------------

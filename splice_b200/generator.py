@@ -186,6 +186,12 @@ class NativeSkip(nn.Sequential):
         return t, flat
 
     def _run_forward(self, xs, keep: bool):
+        if not self.training:
+            # nn.BatchNorm2d in eval mode normalises with the running statistics; the engine implements the training-mode
+            # arithmetic only (the reference never calls .eval(), SURVEY hard part 6). Refuse rather than silently
+            # returning batch-statistics images.
+            raise NotImplementedError("splice_b200's native generator implements BatchNorm in training mode only (the "
+                                      "reference never calls netG.eval()); call netG.train() before using it")
         prepared = []
         for x in xs:
             if x.dim() != 4 or x.shape[1] != 3:

@@ -9,6 +9,7 @@ computes those taps directly (fp32 exports of the qkv GEMM / residual stream). T
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -33,7 +34,10 @@ class VitExtractor:
     QKV_KEY = 'qkv'
     KEY_LIST = [BLOCK_KEY, ATTN_KEY, PATCH_IMD_KEY, QKV_KEY]
 
-    _engines: List[VitEngine] = []
+    # engines alive in this process, weakly held: attn_cosine_sim (a module-level function in the reference) needs one,
+    # but a registry must not keep ~0.7 GB of packed weights + activation pools alive after its LossG is dropped
+    _engines: "weakref.WeakSet[VitEngine]" = weakref.WeakSet()
+    _engine_order = 0
 
     def __init__(self, model_name, device, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  packed: Optional[torch.Tensor] = None):
@@ -54,21 +58,30 @@ class VitExtractor:
 
                 state_dict = random_dino_state_dict(model_name)
             else:
-                self.model = torch.hub.load('facebookresearch/dino:main', model_name).to(device)
+                # the hub module is only the source of the weights: packed on the host side, never kept on the GPU
+                # (`.model` stays available on the CPU for code that inspects it, e.g. `.model.state_dict()`)
+                self.model = torch.hub.load('facebookresearch/dino:main', model_name)
                 self.model.eval()
                 state_dict = self.model.state_dict()
         self.engine = VitEngine(model_name, state_dict, self.device, packed=packed)
-        VitExtractor._engines.append(self.engine)
+        VitExtractor._engine_order += 1
+        self.engine._registry_order = VitExtractor._engine_order
+        VitExtractor._engines.add(self.engine)
         self.hook_handlers = []
         self.layers_dict = {key: list(range(12)) for key in VitExtractor.KEY_LIST}
         self.outputs_dict = {key: [] for key in VitExtractor.KEY_LIST}
 
     @classmethod
     def _engine_for(cls, x: torch.Tensor) -> Optional[VitEngine]:
-        for e in reversed(cls._engines):
-            if e.device == x.device and e.dim == x.shape[-1]:
-                return e
-        return None
+        def idx(d):
+            return d.index if d.index is not None else torch.cuda.current_device()
+
+        best = None
+        for e in list(cls._engines):
+            if e.device.type == x.device.type == "cuda" and idx(e.device) == idx(x.device) and e.dim == x.shape[-1]:
+                if best is None or e._registry_order > best._registry_order:
+                    best = e
+        return best
 
     # ---- taps (ref extractor.py:81-103) ------------------------------------------------------------
     def _run(self, input_img, **want):

@@ -407,20 +407,20 @@ def preprocess_fwd_bwd():
 # ------------------------------------------------------------------------------------------------
 # ViT engine vs oracle
 # ------------------------------------------------------------------------------------------------
-def _engine(name, impl=0):
+def _engine(name, impl=0, stats="init"):
     import torch
     from splice_b200.engine import VitEngine
 
     dino_vit, R = _oracle_on_gpu()
-    model = dino_vit.build(name).cuda()
+    model = dino_vit.build(name, stats=stats).cuda()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     return VitEngine(name, sd, gemm_impl=impl), sd, R
 
 
-def _vit_forward_case(name, hw_list, out_hw, impl=0):
+def _vit_forward_case(name, hw_list, out_hw, impl=0, stats="init", tol=2e-2):
     import torch
 
-    eng, sd, R = _engine(name, impl)
+    eng, sd, R = _engine(name, impl, stats)
     g = torch.Generator(device="cuda").manual_seed(5)
     imgs = [torch.rand(3, h, w, device="cuda", generator=g) for (h, w) in hw_list]
     res = eng.forward(imgs, out_hw, n_grad=0, want_all_qkv=True, want_all_blocks=True)
@@ -432,11 +432,11 @@ def _vit_forward_case(name, hw_list, out_hw, impl=0):
             taps = R.vit_taps(sd, R.global_transform(im, size)[None])
         H = eng.heads
         ref_keys = R.keys_from_qkv(taps["qkv"][11], H).transpose(0, 1).reshape(-1, eng.dim)
-        r = {"model": name, "img": i, "hw": hw_list[i], "impl": impl,
+        r = {"model": name, "img": i, "hw": hw_list[i], "impl": impl, "stats": stats,
              "keys_rel": _rel(res["keys"][i], ref_keys), "cls_rel": _rel(res["cls"][i], taps["block"][-1][0, 0]),
              "qkv0_rel": _rel(res["qkv"][0, i], taps["qkv"][0][0]), "qkv11_rel": _rel(res["qkv"][11, i], taps["qkv"][11][0]),
              "block0_rel": _rel(res["block"][0, i], taps["block"][0][0]), "block11_rel": _rel(res["block"][11, i], taps["block"][11][0])}
-        r["ok"] = all(v < 2e-2 for k, v in r.items() if k.endswith("_rel"))
+        r["ok"] = all(v < tol for k, v in r.items() if k.endswith("_rel"))
         rows.append(r)
     return rows
 
@@ -454,6 +454,15 @@ def vit_forward_s16_simt():
 @check
 def vit_forward_b8():
     return _vit_forward_case("dino_vitb8", [(224, 224), (220, 220)], (224, 224))
+
+
+@check
+def vit_forward_trained_stats():
+    """Same taps with the "trained-statistics" stand-in weights (oracle/dino_vit.py apply_trained_statistics: peaky
+    softmax rows, three residual channels 50-100x the others, non-zero biases, non-unit LayerNorm gains) - the regime
+    real DINO checkpoints put a bf16 pipeline in. Tolerance stated separately: 3e-2 rel-L2 on every tap."""
+    return (_vit_forward_case("dino_vits16", [(224, 224), (213, 213)], (224, 224), stats="trained", tol=3e-2)
+            + _vit_forward_case("dino_vitb8", [(224, 224), (220, 220)], (224, 224), stats="trained", tol=3e-2))
 
 
 @check
@@ -497,11 +506,11 @@ def loss_kernels():
     return out
 
 
-def _vit_loss_backward_case(name, hx, hy, impl=0):
+def _vit_loss_backward_case(name, hx, hy, impl=0, stats="init", tol_loss=5e-3, tol_grad=2e-2):
     """Steady-state objective (ssim + 10 cls + id) through the engine vs the oracle's autograd."""
     import torch
 
-    eng, sd, R = _engine(name, impl)
+    eng, sd, R = _engine(name, impl, stats)
     g = torch.Generator(device="cuda").manual_seed(11)
     A = torch.rand(3, hx, hx, device="cuda", generator=g)
     B = torch.rand(3, hy, hy, device="cuda", generator=g)
@@ -525,12 +534,12 @@ def _vit_loss_backward_case(name, hx, hy, impl=0):
     l_cls = R.cls_loss(sd, xo[None], B[None])
     l_id = R.id_loss(sd, yo[None], B[None])
     (lam["ssim"] * l_ssim + lam["cls"] * l_cls + lam["id"] * l_id).backward()
-    r = {"model": name, "hx": hx, "hy": hy, "impl": impl,
+    r = {"model": name, "hx": hx, "hy": hy, "impl": impl, "stats": stats,
          "ssim": terms[0].item(), "ssim_ref": l_ssim.item(), "cls": terms[1].item(), "cls_ref": l_cls.item(),
          "id": terms[2].item(), "id_ref": l_id.item(), "dX_rel": _rel(dX, xo.grad), "dY_rel": _rel(dY, yo.grad)}
     r["loss_rel"] = max(abs(r["ssim"] - r["ssim_ref"]) / abs(r["ssim_ref"]), abs(r["cls"] - r["cls_ref"]) / abs(r["cls_ref"]),
                         abs(r["id"] - r["id_ref"]) / abs(r["id_ref"]))
-    r["ok"] = r["loss_rel"] < 5e-3 and r["dX_rel"] < 2e-2 and r["dY_rel"] < 2e-2
+    r["ok"] = r["loss_rel"] < tol_loss and r["dX_rel"] < tol_grad and r["dY_rel"] < tol_grad
     return [r]
 
 
@@ -549,8 +558,58 @@ def vit_loss_backward_b8():
     return _vit_loss_backward_case("dino_vitb8", 224, 217)
 
 
+@check
+def vit_loss_backward_trained_stats():
+    """Objective + d loss / d image with the trained-statistics stand-in weights (see vit_forward_trained_stats).
+    Stated tolerance for this regime: losses 1e-2 rel, gradients 4e-2 rel-L2."""
+    return (_vit_loss_backward_case("dino_vits16", 128, 125, stats="trained", tol_loss=1e-2, tol_grad=4e-2)
+            + _vit_loss_backward_case("dino_vitb8", 224, 217, stats="trained", tol_loss=1e-2, tol_grad=4e-2))
 
-def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width=None):
+
+
+def _oracle_step_lowmem(R, vsd, cfg, lam, gsd, inputs, want_entire):
+    """The oracle's step evaluated term by term and crop by crop (backward after each): the objective is a plain sum
+    over terms and crops (ref losses.py:46-105), so the gradients accumulate to the same values while only one ViT
+    autograd graph (12 layers of materialised [H,t,t] probabilities: 17 GB at t = 3137) is alive at a time.
+    Returns (losses, generated images with .grad)."""
+    import torch
+
+    size = cfg["dino_global_patch_size"]
+    srcs = {"x_global": "A_global", "y_global": "B_global"}
+    if want_entire:
+        srcs["x_entire"] = "A"
+    outs = {k: R.generator_forward(gsd, inputs[v]) for k, v in srcs.items()}
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in outs.items()}
+    losses, total = {}, 0.0
+    plan = [("loss_global_ssim", "lambda_global_ssim", R.ssim_loss, "x_global", "A_global"),
+            ("loss_entire_ssim", "lambda_entire_ssim", R.ssim_loss, "x_entire", "A"),
+            ("loss_entire_cls", "lambda_entire_cls", R.cls_loss, "x_entire", "B_global"),
+            ("loss_global_cls", "lambda_global_cls", R.cls_loss, "x_global", "B_global"),
+            ("loss_global_id_B", "lambda_global_identity", R.id_loss, "y_global", "B_global")]
+    for name, lk, fn, ok, ik in plan:
+        if lam[lk] <= 0:
+            continue
+        acc = 0.0
+        for i in range(min(len(leaves[ok]), len(inputs[ik]))):
+            term = fn(vsd, leaves[ok][i:i + 1], inputs[ik][i:i + 1], size)
+            (term * lam[lk]).backward()
+            acc += float(term.detach())
+            del term
+            torch.cuda.empty_cache()
+        losses[name] = acc
+        total += acc * lam[lk]
+    losses["loss"] = total
+    for k, v in outs.items():
+        v.retain_grad()
+    torch.autograd.backward([outs[k] for k in outs if leaves[k].grad is not None],
+                            [leaves[k].grad for k in outs if leaves[k].grad is not None])
+    for k in outs:
+        outs[k].grad_ref = leaves[k].grad
+    return losses, outs
+
+
+def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width=None, stats="init", lowmem=False,
+                      tol_loss=5e-3, tol_dout=2e-2, tol_pgrad=3e-2):
     """One full optimisation step (netG on every crop batch -> LossG -> backward) at the shapes of a BASELINE.json
     config, against the oracle evaluated in fp32 on the same device: per-term losses, d loss / d generated images,
     netG parameter gradients. Teacher-forced (same parameters, same inputs)."""
@@ -564,7 +623,7 @@ def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width
 
     cfg = make_cfg(name)
     cfg.update(dino_global_patch_size=vit_size, global_A_crops_n_crops=n_crops, global_B_crops_n_crops=n_crops)
-    vit = dino_vit.build(name).cuda()
+    vit = dino_vit.build(name, stats=stats).cuda()
     vsd = {k: v.detach() for k, v in vit.state_dict().items()}
     torch.manual_seed(0)
     model = Model(cfg)
@@ -600,14 +659,19 @@ def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width
     sd = {k: v.detach().clone() for k, v in model.netG.state_dict().items()}
     params = {k: sd[k].requires_grad_(True) for k, _ in model.netG.named_parameters()}
     lam = R.active_lambdas(cfg, step, R.active_lambdas(cfg, 1, None))
-    outs_ref = {"x_global": R.generator_forward(sd, inputs["A_global"]), "y_global": R.generator_forward(sd, inputs["B_global"])}
-    if "x_entire" in outputs:
-        outs_ref["x_entire"] = R.generator_forward(sd, inputs["A"])
-    for v in outs_ref.values():
-        v.retain_grad()
-    ref = R.loss_g(vsd, cfg, lam, outs_ref, inputs)
-    ref["loss"].backward()
-    r = {"model": name, "side": side, "n_crops": n_crops, "vit_size": vit_size, "step": step,
+    if lowmem:
+        ref, outs_ref = _oracle_step_lowmem(R, vsd, cfg, lam, sd, inputs, "x_entire" in outputs)
+        ref_dout = {k: outs_ref[k].grad_ref for k in outs_ref}
+    else:
+        outs_ref = {"x_global": R.generator_forward(sd, inputs["A_global"]), "y_global": R.generator_forward(sd, inputs["B_global"])}
+        if "x_entire" in outputs:
+            outs_ref["x_entire"] = R.generator_forward(sd, inputs["A"])
+        for v in outs_ref.values():
+            v.retain_grad()
+        ref = R.loss_g(vsd, cfg, lam, outs_ref, inputs)
+        ref["loss"].backward()
+        ref_dout = {k: outs_ref[k].grad for k in outs_ref}
+    r = {"model": name, "side": side, "n_crops": n_crops, "vit_size": vit_size, "step": step, "stats": stats,
          "crop_sizes": [int(inputs["A_global"].shape[-1]), int(inputs["B_global"].shape[-1])]}
     worst = 0.0
     for k, v in ref.items():
@@ -616,14 +680,28 @@ def _config_step_case(name, side, n_crops, vit_size, step=1, crop_lo=0.95, width
         worst = max(worst, e)
     r["loss_rel"] = worst
     r["pix_maxabs"] = max(_maxabs(outputs[k], outs_ref[k]) for k in outputs)
-    r["dout_rel"] = max(_rel(outputs[k].grad, outs_ref[k].grad) for k in outputs if outputs[k].grad is not None)
+    r["dout_rel"] = max(_rel(outputs[k].grad, ref_dout[k]) for k in outputs if outputs[k].grad is not None)
     num = sum(float((p.grad - params[k].grad).double().pow(2).sum()) for k, p in model.netG.named_parameters())
     den = sum(float(params[k].grad.double().pow(2).sum()) for k, _ in model.netG.named_parameters())
     r["pgrad_rel"] = (num / max(den, 1e-300)) ** 0.5
     # stated tolerances (bf16 tensor-core ViT vs fp32 oracle): losses 5e-3 rel, d loss / d image 2e-2 rel-L2, generated pixels
     # 1e-4 abs, netG gradients 3e-2 rel-L2 over all parameters (they inherit the d loss / d image error)
-    r["ok"] = r["loss_rel"] < 5e-3 and r["dout_rel"] < 2e-2 and r["pix_maxabs"] < 1e-4 and r["pgrad_rel"] < 3e-2
+    r["ok"] = r["loss_rel"] < tol_loss and r["dout_rel"] < tol_dout and r["pix_maxabs"] < 1e-4 and r["pgrad_rel"] < tol_pgrad
     return [r]
+
+
+@check
+def config2_step_224():
+    """BASELINE.json configs[1] (the headline config) as one full step: 224x224 pair, ViT-B/8, crops 213-224 px,
+    a steady-state step and an "entire image" step."""
+    return _config_step_case("dino_vitb8", 224, 1, 224, step=2) + _config_step_case("dino_vitb8", 224, 1, 224, step=75)
+
+
+@check
+def config2_step_224_trained_stats():
+    """configs[1] full step with the trained-statistics stand-in ViT weights (peaky softmax, outlier channels).
+    Stated tolerance for this regime: losses 1e-2 rel, d loss / d image 4e-2, netG gradients 5e-2 rel-L2."""
+    return _config_step_case("dino_vitb8", 224, 1, 224, step=2, stats="trained", tol_loss=1e-2, tol_dout=4e-2, tol_pgrad=5e-2)
 
 
 @check
@@ -651,6 +729,14 @@ def config5_step_multicrop_448vit():
     """BASELINE.json configs[4] at a bounded size: multi-crop batches (2 crops per batch, BatchNorm statistics over the
     crops) of a 512 px pair with the ViT run at 448 px (t = 3137: the N^2 stress of the self-similarity / attention)."""
     return _config_step_case("dino_vitb8", 512, 2, 448, step=2)
+
+
+@check
+def config5_step_full_896():
+    """BASELINE.json configs[4] at its stated size: 896x896 pair, 4 + 4 crops of 851-896 px per step (BatchNorm statistics
+    over the 4 crops), ViT-B/8 at 448 px (t = 3137: S [3137,3137], 472 MB of attention probabilities per layer in the
+    reference). The oracle is evaluated crop by crop (same sums, bounded memory)."""
+    return _config_step_case("dino_vitb8", 896, 4, 448, step=2, lowmem=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -709,23 +795,165 @@ def train_step_golden():
             errs.append(((a - b).norm() / b.norm().clamp_min(1e-20)).item())
         r["netG_grad_rel_max"] = max(errs)
         r["netG_grad_rel_med"] = sorted(errs)[len(errs) // 2]
-        r["ok"] = r["loss_rel"] < 5e-3 and r["dx_rel"] < 2e-2 and r["netG_grad_rel_med"] < 2e-2
+        # gates: the median AND the worst tensor of the sampled netG gradients (bf16 ViT vs the fp32 reference)
+        r["ok"] = r["loss_rel"] < 5e-3 and r["dx_rel"] < 2e-2 and r["netG_grad_rel_med"] < 2e-2 and r["netG_grad_rel_max"] < 6e-2
         if step == 1:
             opt = get_optimizer(cfg, model.netG.parameters())
             opt.step()
             torch.cuda.synchronize()
+            # beta1 = 0 makes the first Adam step a sign step of size lr (every entry moves by +-lr), so "|delta| <= 2 lr"
+            # holds for ANY gradient: what is gated is the fraction of sampled entries that moved the SAME way as in the
+            # reference (only entries whose gradient is ~0 relative to the bf16 error may flip), overall and among the
+            # entries whose reference gradient is not small (>= 10 % of the tensor's rms: those must all agree), on the
+            # weights that do not feed a BatchNorm-cancelled bias (SURVEY.md hard part 1)
+            lr = cfg["lr"]
+            n_all = n_agree = n_big = n_big_agree = 0
             perr = []
             for k, p in model.netG.named_parameters():
                 if k.endswith(".bias") and k[:-5].endswith(".0") and not k.startswith("9."):
                     continue
-                a, b = _sample(p, rec["post_adam"][k]), rec["post_adam"][k]["samples"]
+                summ = rec["post_adam"][k]
+                a, b = _sample(p, summ), summ["samples"]
+                g_ref = rec["grads"][k]["samples"]
+                assert torch.equal(rec["grads"][k]["idx"], summ["idx"])
                 perr.append((a - b).abs().max().item())
-            # beta1 = 0 makes the first Adam step a sign step of size lr: entries whose gradient sign flips under
-            # bf16 rounding move by 2*lr; report the fraction instead of a norm
+                same = (a - b).abs() < 0.5 * lr
+                big = g_ref.abs() >= 0.1 * g_ref.pow(2).mean().sqrt()
+                n_all += same.numel(); n_agree += int(same.sum())
+                n_big += int(big.sum()); n_big_agree += int((same & big).sum())
             r["post_adam_maxabs"] = max(perr)
-            r["ok"] = r["ok"] and r["post_adam_maxabs"] <= 2 * cfg["lr"] * 1.01
+            r["adam_sign_agree"] = n_agree / max(n_all, 1)
+            r["adam_sign_agree_big"] = n_big_agree / max(n_big, 1)
+            r["adam_samples"] = [n_all, n_big]
+            r["ok"] = (r["ok"] and r["post_adam_maxabs"] <= 2 * lr * 1.01 and r["adam_sign_agree"] >= 0.985
+                       and r["adam_sign_agree_big"] >= 0.999)
         out.append(r)
     return out
+
+
+@check
+def free_running_loss_band():
+    """Loop-level statistical parity (SURVEY §7 hard part 1): trajectories are chaotic (beta1 = 0 Adam is a sign descent),
+    so free-running runs cannot be compared step by step. 300 steps at configs[0] shapes (128 px pair, ViT-S/16) over 3
+    seeds (netG init + crop schedule), splice_b200 (bf16 tensor-core ViT, native generator, fused Adam) against the fp32
+    oracle loop on the same device, same schedule of crops and lambda schedule. Compared: the loss curve in windows of
+    25 steps (the product's window means must stay inside the oracle's across-seed envelope widened by 25 %) and the
+    final loss (mean of the last 50 steps: across-seed means within 10 % or 2 sigma of the oracle's seeds)."""
+    import numpy as np
+    import torch
+
+    dino_vit, R = _oracle_on_gpu()
+    from bench import make_cfg, synth_image, crop_schedule
+    from splice_b200.models.model import Model
+    from splice_b200.models.networks import define_G
+    from splice_b200.util.losses import LossG
+    from splice_b200.util.util import get_optimizer
+
+    n_steps, win, seeds = 300, 25, (0, 1, 2)
+    cfg = make_cfg("dino_vits16")
+    vsd = {k: v.detach() for k, v in dino_vit.build("dino_vits16").cuda().state_dict().items()}
+    A, B = synth_image(1000, 128, 8), synth_image(1001, 128, 16)
+    A_dev = A[None].cuda()
+    every = cfg["entire_A_every"]
+    crit = LossG(cfg, state_dict=vsd)
+    curves = {"gpu": [], "ref": []}
+    for seed in seeds:
+        sched = [(a.cuda(), b.cuda()) for a, b in crop_schedule(A, B, 16, seed=seed)]
+        # ---- product loop
+        torch.manual_seed(seed)
+        model = Model(cfg)
+        init_sd = {k: v.detach().clone() for k, v in model.netG.state_dict().items()}
+        opt = get_optimizer(cfg, model.netG.parameters())
+        crit.lambdas.update(lambda_global_ssim=0, lambda_global_identity=0, lambda_entire_ssim=0, lambda_entire_cls=0)
+        vals = []
+        for i in range(n_steps):
+            a, b = sched[i % len(sched)]
+            inputs = {"step": torch.tensor([float(i)]), "A_global": a, "B_global": b}
+            if i % every == 0:
+                inputs["A"] = A_dev
+            opt.zero_grad()
+            losses = crit(model(inputs), inputs)
+            losses["loss"].backward()
+            opt.step()
+            vals.append(losses["loss"].detach())
+        curves["gpu"].append(torch.stack(vals).float().cpu().numpy())
+        # ---- oracle loop (fp32, same init, same crops)
+        params = {k: init_sd[k].clone().requires_grad_(True) for k, _ in model.netG.named_parameters()}
+        bufs = {k: v.clone() for k, v in init_sd.items() if k not in params}
+        m = {k: torch.zeros_like(p) for k, p in params.items()}
+        v = {k: torch.zeros_like(p) for k, p in params.items()}
+        lam, vals = None, []
+        for i in range(n_steps):
+            a, b = sched[i % len(sched)]
+            inputs = {"A_global": a, "B_global": b, "A": A_dev}
+            lam = R.active_lambdas(cfg, i, lam)
+            sd = {**bufs, **params}
+            outs = {"x_global": R.generator_forward(sd, a), "y_global": R.generator_forward(sd, b)}
+            if i % every == 0:
+                outs["x_entire"] = R.generator_forward(sd, A_dev)
+            loss = R.loss_g(vsd, cfg, lam, outs, inputs)["loss"]
+            grads = torch.autograd.grad(loss, list(params.values()))
+            with torch.no_grad():
+                for (k, p), g in zip(params.items(), grads):
+                    R.adam_step(p, g, m[k], v[k], i + 1, cfg["lr"], cfg["optimizer_beta1"], cfg["optimizer_beta2"])
+            vals.append(loss.detach())
+        curves["ref"].append(torch.stack(vals).float().cpu().numpy())
+    gpu, ref = np.stack(curves["gpu"]), np.stack(curves["ref"])                    # [seeds, steps]
+    steady = np.array([i for i in range(n_steps) if i % every != 0 and i >= 2])    # same set of active terms
+    wins = [steady[(steady >= w0) & (steady < w0 + win)] for w0 in range(0, n_steps, win)]
+    gw = np.stack([gpu[:, w].mean(1) for w in wins], 1)                            # [seeds, windows]
+    rw = np.stack([ref[:, w].mean(1) for w in wins], 1)
+    lo, hi = rw.min(0), rw.max(0)
+    pad = 0.25 * (0.5 * (lo + hi))
+    inside = (gw >= lo - pad) & (gw <= hi + pad)
+    tail = steady[steady >= n_steps - 50]
+    gf, rf = gpu[:, tail].mean(1), ref[:, tail].mean(1)
+    tol = max(0.10 * rf.mean(), 2.0 * rf.std())
+    r = {"seeds": list(seeds), "steps": n_steps, "window": win,
+         "loss_first_window": [float(gw[:, 0].mean()), float(rw[:, 0].mean())],
+         "loss_final_gpu": [float(x) for x in gf], "loss_final_ref": [float(x) for x in rf],
+         "final_gap": float(abs(gf.mean() - rf.mean())), "final_tol": float(tol),
+         "windows_inside_band": float(inside.mean()), "curve_gpu": [float(x) for x in gw.mean(0)],
+         "curve_ref": [float(x) for x in rw.mean(0)],
+         "decreased": bool(gw[:, -1].mean() < 0.8 * gw[:, 0].mean())}
+    r["ok"] = bool(r["final_gap"] <= tol and r["windows_inside_band"] >= 0.9 and np.isfinite(gpu).all() and r["decreased"])
+    return [r]
+
+
+@check
+def extractor_attn_taps():
+    """VitExtractor's list-returning compatibility taps (ref extractor.py:81-103) against the oracle on one image:
+    12 block outputs, 12 qkv outputs, 12 post-softmax attention maps [1,H,t,t], and the keys / self-similarity helpers."""
+    import torch
+
+    dino_vit, R = _oracle_on_gpu()
+    from splice_b200.models.extractor import VitExtractor, attn_cosine_sim
+
+    name = "dino_vits16"
+    vsd = {k: v.detach() for k, v in dino_vit.build(name).cuda().state_dict().items()}
+    ext = VitExtractor(name, "cuda", state_dict=vsd)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = R.global_transform(torch.rand(3, 200, 200, device="cuda", generator=g), 224)[None]
+    with torch.no_grad():
+        taps = R.vit_taps(vsd, img)
+    blocks, qkvs, attns = ext.get_feature_from_input(img), ext.get_qkv_feature_from_input(img), ext.get_attn_feature_from_input(img)
+    keys = ext.get_keys_from_input(img, 11)
+    ssim = ext.get_keys_self_sim_from_input(img, 11)
+    H = ext.get_head_num()
+    ref_keys = R.keys_from_qkv(taps["qkv"][11], H)
+    t = ref_keys.shape[1]
+    ref_ssim = R.attn_cosine_sim(ref_keys.transpose(0, 1).reshape(t, -1)[None, None])
+    r = {"n": [len(blocks), len(qkvs), len(attns)], "attn_shape": list(attns[0].shape),
+         "block_rel": max(_rel(blocks[i], taps["block"][i]) for i in range(12)),
+         "qkv_rel": max(_rel(qkvs[i], taps["qkv"][i]) for i in range(12)),
+         "attn_maxabs": max(_maxabs(attns[i], taps["attn"][i]) for i in range(12)),
+         "attn_rowsum_err": max((attns[i].sum(-1) - 1).abs().max().item() for i in range(12)),
+         "keys_rel": _rel(keys, ref_keys), "ssim_maxabs": _maxabs(ssim, ref_ssim),
+         "cos_api_maxabs": _maxabs(attn_cosine_sim(ref_keys.transpose(0, 1).reshape(t, -1)[None, None].contiguous()), ref_ssim)}
+    r["ok"] = (r["n"] == [12, 12, 12] and r["attn_shape"] == [1, H, t, t] and r["block_rel"] < 2e-2 and r["qkv_rel"] < 2e-2
+               and r["attn_maxabs"] < 5e-3 and r["attn_rowsum_err"] < 1e-5 and r["keys_rel"] < 2e-2 and r["ssim_maxabs"] < 5e-3
+               and r["cos_api_maxabs"] < 1e-4)
+    return [r]
 
 
 @check
