@@ -1143,6 +1143,13 @@ def train_loop_smoke():
 # ------------------------------------------------------------------------------------------------
 # native generator vs the same module tree evaluated with torch ops (fp32, TF32 off) and vs the oracle
 # ------------------------------------------------------------------------------------------------
+def _torch_ops(net, x):
+    """the generator's module tree evaluated module by module with torch ops (isolates engine bugs)"""
+    import torch
+
+    return torch.nn.Sequential.forward(net, x)
+
+
 def _generator_case(N, H, W, seed=0):
     import copy
     import torch
@@ -1167,17 +1174,17 @@ def _generator_case(N, H, W, seed=0):
     out.backward(gout)
     out2 = net(x)                  # second call in the same step: gradients must accumulate
     out2.backward(0.5 * gout)
-    ro = ref.forward_reference_ops(x)
+    ro = _torch_ops(ref, x)
     ro.backward(gout)
-    ro2 = ref.forward_reference_ops(x)
+    ro2 = _torch_ops(ref, x)
     ro2.backward(0.5 * gout)
     # fp64 evaluation of the same tree: separates kernel bugs from the ill-conditioning of BatchNorm chains
     ref64 = copy.deepcopy(ref).double()
     for q in ref64.parameters():
         q.grad = None
-    r64 = ref64.forward_reference_ops(x.double())
+    r64 = _torch_ops(ref64, x.double())
     r64.backward(gout.double())
-    r64b = ref64.forward_reference_ops(x.double())
+    r64b = _torch_ops(ref64, x.double())
     r64b.backward(0.5 * gout.double())
     torch.cuda.synchronize()
     sd = {k: v.detach() for k, v in ref.state_dict().items()}
@@ -1229,7 +1236,7 @@ def _generator_exact_case(H, W):
     x = torch.rand(1, 3, H, W, device="cuda", generator=g)
     gout = torch.randn(1, 3, H, W, device="cuda", generator=g)
     net(x).backward(gout)
-    ref64.forward_reference_ops(x.double()).backward(gout.double())
+    _torch_ops(ref64, x.double()).backward(gout.double())
     errs = {}
     for (k, p), (_, q) in zip(net.named_parameters(), ref64.named_parameters()):
         if k.endswith(".0.bias") and not k.startswith("9."):
