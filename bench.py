@@ -8,7 +8,8 @@ structure and appearance crops, the DINO-ViT objective (key self-similarity + [C
 "entire image" terms every 75th step), backward into netG, Adam. Default workload (--config 2) = BASELINE.json
 configs[1] (224x224 pair, DINO ViT-B/8), the configuration the metric is quoted on; --config 3 / 5 / 1 time
 configs[2] (448 px pair), configs[4] (896 px pair, 4 crops per batch, ViT at 448 px: t = 3137) and configs[0]
-(128 px pair, ViT-S/16). Synthetic pair per SURVEY.md §8d, seeded random DINO-style ViT weights (no network for
+(128 px pair, ViT-S/16); --config 6 is the reference's default full-resolution regime (1200x900 pair, A_resize: -1).
+Synthetic pair per SURVEY.md §8d, seeded random DINO-style ViT weights (no network for
 checkpoints). With N GPUs every rank optimises its own pair (weak scaling, no data-path collective; one NCCL
 broadcast of the packed ViT weights at start-up); `value` is then the aggregate over the N pairs.
 
@@ -41,6 +42,10 @@ WORKLOADS = {
     2: {"tag": "configs[1]", "model": "dino_vitb8", "side": 224, "n_crops": 1, "vit_size": 224, "sched": 32},
     3: {"tag": "configs[2]", "model": "dino_vitb8", "side": 448, "n_crops": 1, "vit_size": 224, "sched": 32},
     5: {"tag": "configs[4]", "model": "dino_vitb8", "side": 896, "n_crops": 4, "vit_size": 448, "sched": 6},
+    # not a BASELINE.json config: the reference's DEFAULT regime (conf/default/config.yaml:5-6 A_resize: -1) on a pair of the
+    # shipped size, 1200 x 900 (W x H) - SURVEY.md §8f rank 3: netG at 855-900 px, x_entire at 900x1200, its ViT input 224x298
+    6: {"tag": "default full-resolution regime (A_resize: -1)", "model": "dino_vitb8", "side": 900, "width": 1200, "n_crops": 1,
+        "vit_size": 224, "sched": 16},
 }
 VIT_ARCH = {"dino_vits16": (16, 384), "dino_vitb8": (8, 768)}   # patch, D (depth 12)
 VIT_LABEL = {"dino_vits16": "ViT-S/16", "dino_vitb8": "ViT-B/8"}
@@ -64,7 +69,7 @@ def vit_gflop_per_step(w: dict) -> float:
 def workload_string(w: dict) -> str:
     """One description for BOTH arms (the driver compares the strings)."""
     lo = int(round(0.95 * w["side"]))
-    return (f"{w['tag']}: {w['side']}x{w['side']} pair, DINO {VIT_LABEL[w['model']]}, "
+    return (f"{w['tag']}: {w.get('width', w['side'])}x{w['side']} pair, DINO {VIT_LABEL[w['model']]}, "
             f"{w['n_crops']} crop(s) of {lo}-{w['side']} px per batch, ViT input {w['vit_size']} px (t = {vit_tokens(w)}), reference step "
             f"schedule: the timed steps start right after an 'entire image' step, every {ENTIRE_EVERY}th step adds the entire-image terms")
 
@@ -78,6 +83,14 @@ def synth_image(seed: int, side: int, grid: int) -> torch.Tensor:
     img = np.asarray(Image.fromarray(low).resize((side, side), Image.BICUBIC)).astype(np.float64)
     img = np.clip(img + rng.normal(0, 8, img.shape), 0, 255).astype(np.uint8)
     return torch.from_numpy(img).permute(2, 0, 1).float() / 255.0
+
+
+def synth_pair(w: dict, k: int = 0):
+    """Pair k of a workload: (A, B) as [3, side, width] (square unless the workload names a width)."""
+    side, width = w["side"], w.get("width", w["side"])
+    big = max(side, width)
+    A, B = synth_image(1000 + 2 * k, big, 8), synth_image(1001 + 2 * k, big, 16)
+    return A[:, :side, :width].contiguous(), B[:, :side, :width].contiguous()
 
 
 def make_cfg(model_name: str) -> dict:
@@ -96,11 +109,11 @@ def crop_schedule(A: torch.Tensor, B: torch.Tensor, n: int, seed: int, min_cover
     for _ in range(n):
         pair = []
         for img in (A, B):
-            h = img.shape[1]
-            s = int(round(rng.uniform(min_cover * h, h)))
+            h, wd = img.shape[1], img.shape[2]
+            s = min(int(round(rng.uniform(min_cover * h, h))), wd)
             crops = []
             for _ in range(n_crops):
-                y, x = rng.integers(0, h - s + 1), rng.integers(0, h - s + 1)
+                y, x = rng.integers(0, h - s + 1), rng.integers(0, wd - s + 1)
                 crops.append(img[:, y:y + s, x:x + s])
             pair.append(torch.stack(crops).contiguous())
         out.append(tuple(pair))
@@ -177,7 +190,7 @@ class OracleLoop:
         self.params = {k: v.to(self.dev).requires_grad_(True) for k, v in R.generator_init_state(seed, self.cfg["init_gain"]).items()}
         self.m = {k: torch.zeros_like(p) for k, p in self.params.items()}
         self.v = {k: torch.zeros_like(p) for k, p in self.params.items()}
-        A, B = synth_image(1000, w["side"], 8), synth_image(1001, w["side"], 16)
+        A, B = synth_pair(w, 0)
         self.A = A[None].to(self.dev)
         self.sched = [(a.to(self.dev), b.to(self.dev)) for a, b in crop_schedule(A, B, min(w["sched"], 8), seed=0, n_crops=w["n_crops"])]
         self.lam = R.active_lambdas(self.cfg, 1, None)
@@ -305,7 +318,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     crit = LossG(cfg, packed=packed)
     opt = get_optimizer(cfg, model.netG.parameters())
 
-    A, B = synth_image(1000 + 2 * rank, side, 8), synth_image(1001 + 2 * rank, side, 16)
+    A, B = synth_pair(w, rank)
     sched_host = [(a.pin_memory(), b.pin_memory()) for a, b in crop_schedule(A, B, w["sched"], seed=rank, n_crops=w["n_crops"])]
     sched_dev = [(a.to(dev), b.to(dev)) for a, b in sched_host]
     A_host, A_dev = A[None].pin_memory(), A[None].to(dev)

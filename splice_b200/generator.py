@@ -282,9 +282,6 @@ class NativeSkip(nn.Sequential):
     def forward(self, input):
         return self.forward_many([input])[0]
 
-    def forward_reference_ops(self, input):
-        """The same tree evaluated module by module with torch ops (tests only: isolates engine bugs)."""
-        return nn.Sequential.forward(self, input)
 
     def __del__(self):
         eng = getattr(self, "_eng", None)

@@ -15,6 +15,7 @@ import yaml
 from tqdm import tqdm
 
 from .data.Dataset import SingleImageDataset
+from .data.device_aug import DeviceAugmentedDataset
 from .data.prefetch import PrefetchedSamples
 from .models.model import Model
 from .util.losses import LossG
@@ -45,7 +46,12 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     torch.manual_seed(seed)
     print(f'running with seed: {seed}.')
 
-    dataset = SingleImageDataset(cfg)
+    # cfg['device_aug']: the same random draws, the image arithmetic on the GPU (data/device_aug.py) - the only feed that keeps
+    # up with the step rate on full-size (1200x900) pairs; default: the reference's PIL pipeline
+    if cfg.get('device_aug', False) and torch.cuda.is_available():
+        dataset = DeviceAugmentedDataset(cfg, device)
+    else:
+        dataset = SingleImageDataset(cfg)
     model = Model(cfg)
     criterion = LossG(cfg, state_dict=vit_state_dict)
     optimizer = get_optimizer(cfg, model.netG.parameters())

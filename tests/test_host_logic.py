@@ -201,3 +201,50 @@ def test_prefetched_samples_reproduce_the_inline_stream(tmp_path):
             assert torch.equal(a[k], b[k]), k
     assert "A" in got[0] and "A" in got[75] and "A" not in got[1]
     assert [float(g["step"]) for g in got] == [float(i) for i in range(n)]
+
+
+def test_device_aug_feed_consumes_the_reference_random_stream(tmp_path):
+    """data/device_aug.py: same random PARAMETERS as the PIL pipeline (generator states identical after every sample,
+    identical crop shapes), pixel arithmetic within the documented bounds of the PIL arithmetic (run on the CPU here:
+    the feed only needs a torch device)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from bench import make_cfg, synth_image
+    from splice_b200.data.Dataset import SingleImageDataset
+    from splice_b200.data.device_aug import DeviceAugmentedDataset
+
+    for sub, seed, grid in (("A", 1000, 8), ("B", 1001, 16)):
+        (tmp_path / sub).mkdir()
+        t = synth_image(seed, 200, grid)[:, :150, :200]                      # non-square, like the shipped pairs
+        Image.fromarray((t.permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)).save(tmp_path / sub / "im.png")
+    cfg = make_cfg("dino_vitb8")
+    cfg.update(dataroot=str(tmp_path), global_A_crops_n_crops=2, global_B_crops_n_crops=2, entire_A_every=7)
+
+    def run(make):
+        np.random.seed(5)
+        torch.manual_seed(5)
+        ds = make()
+        out = []
+        for _ in range(40):
+            s = ds[0]
+            out.append(({k: v.clone().cpu() for k, v in s.items()}, torch.get_rng_state().clone(), np.random.get_state()[1].copy()))
+        return out
+
+    ref = run(lambda: SingleImageDataset(cfg))
+    got = run(lambda: DeviceAugmentedDataset(cfg, device="cpu"))
+    worst = mean = 0.0
+    for (sa, ta, na), (sb, tb, nb) in zip(ref, got):
+        assert torch.equal(ta, tb) and (na == nb).all()          # the same draws were made, in the same order
+        assert sa.keys() == sb.keys()
+        for k in sa:
+            assert sa[k].shape == sb[k].shape, k
+            d = (sa[k].float() - sb[k].float()).abs()
+            worst, mean = max(worst, d.max().item()), max(mean, d.mean().item())
+    assert torch.equal(ref[-1][0]["step"], got[-1][0]["step"])
+    assert any("A" in s for s, _, _ in got)
+    assert mean < 3 / 255 and worst < 24 / 255, (mean * 255, worst * 255)
+    # the texture image is only flipped and cropped: exact
+    for (sa, _, _), (sb, _, _) in zip(ref, got):
+        assert torch.equal(sa["B_global"], sb["B_global"])
