@@ -195,6 +195,12 @@ SPLICE_API int splice_gen_set_graphs(void* ctx, int on);
  * accumulate != 0: p->grad += (autograd's accumulation over the 2-3 netG calls of a step); accumulate == 0: p->grad = (every
  * element is written). Calls on different slots may run concurrently on different streams when given disjoint grad tables. */
 SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const void* dout, int slot, int accumulate, void* stream);
+/* test hook, not on the product path: ONE stride-1 "same" convolution of the generator (K = 1 or 3, weights [Cout,Cin,K,K] as
+ * nn.Conv2d stores them) or its data gradient, on the shared-memory-tiled kernel family (tiled != 0) or the direct one, without
+ * producer BatchNorm / statistics. dgrad == 0: y[N,Cout,H,W] = conv(x[N,Cin,H,W]) + bias; dgrad != 0: x is d y [N,Cout,H,W] and
+ * y receives d x [N,Cin,H,W]. ref: nn.Conv2d built by models/unet/common.py:99-124 */
+SPLICE_API int splice_gen_debug_conv(const void* x, int N, int Cin, int H, int W, const void* w, int Cout, int K, const void* bias,
+                                     void* y, int dgrad, int tiled, void* stream);
 /* dst[i] += srcs[0][i] + ... + srcs[n_src-1][i] (fp32, fixed order, n_src <= 4): folds the per-call gradient buffers of
  * concurrently executed netG backward passes into .grad (ref: autograd gradient accumulation, train.py:56,78) */
 SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, size_t n, void* stream);

@@ -150,6 +150,8 @@ splice_gen_forward = _sig("splice_gen_forward", c_int,
 splice_gen_update_running = _sig("splice_gen_update_running", c_int, [c_void_p, C.POINTER(SpliceGenPointers), c_int, c_void_p])
 splice_gen_set_graphs = _sig("splice_gen_set_graphs", c_int, [c_void_p, c_int])
 splice_gen_backward = _sig("splice_gen_backward", c_int, [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_int, c_void_p])
+splice_gen_debug_conv = _sig("splice_gen_debug_conv", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                                               c_void_p, c_int, c_int, c_void_p])
 splice_accumulate = _sig("splice_accumulate", c_int, [c_void_p, C.POINTER(c_void_p), c_int, c_size_t, c_void_p])
 splice_adam_step = _sig("splice_adam_step", c_int,
                         [C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
@@ -164,7 +166,7 @@ EXPORTS = [
     "splice_vit_packed_floats", "splice_vit_create", "splice_vit_destroy", "splice_vit_forward", "splice_vit_backward",
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total", "splice_debug_spin",
     "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward", "splice_gen_set_graphs",
-    "splice_accumulate", "splice_gen_update_running",
+    "splice_accumulate", "splice_gen_update_running", "splice_gen_debug_conv",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
 

@@ -327,6 +327,13 @@ SPLICE_API int splice_gen_backward(void* ctx, const SpliceGenPointers* p, const 
     for (int i = 0; i < GEN_PARAMS; ++i) SPLICE_REQUIRE(g.param[i] && g.grad[i], "splice_gen_backward: parameter/grad %d is null", i);
     return static_cast<GenEngine*>(ctx)->backward(g, (const float*)dout, slot, accumulate != 0, (cudaStream_t)stream);
 }
+SPLICE_API int splice_gen_debug_conv(const void* x, int N, int Cin, int H, int W, const void* w, int Cout, int K, const void* bias,
+                                     void* y, int dgrad, int tiled, void* stream) {
+    SPLICE_REQUIRE(x && w && y && N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "splice_gen_debug_conv: bad argument");
+    SPLICE_REQUIRE(dgrad || bias, "splice_gen_debug_conv: the forward needs a bias");
+    return gen_debug_conv((const float*)x, N, Cin, H, W, (const float*)w, Cout, K, (const float*)bias, (float*)y, dgrad, tiled,
+                          (cudaStream_t)stream);
+}
 SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, size_t n, void* stream) {
     SPLICE_REQUIRE(dst && srcs && n_src > 0 && n_src <= ACC_MAX_SRC && n > 0, "splice_accumulate: bad argument");
     AccTable t;

@@ -753,6 +753,228 @@ __global__ void __launch_bounds__(256) cat_bwd_up_kernel(const float* __restrict
 }
 
 // -------------------------------------------------------------------------------------------------
+// Tiled stride-1 "same" convolution for the HIGH-RESOLUTION layers (K = 3 or 1), forward and data gradient.
+//   The direct kernels above fetch every tap from global / L1 and keep one pixel per thread: fine for the
+//   latency-bound low-resolution layers, ~10-20 % of the FP32 FMA rate once a layer has enough pixels to be
+//   throughput-bound (netG at 448 / 896 px: 10 ms and 35 ms per step). Here a CTA owns a TR x 32 output tile x 16
+//   output channels: the input tile (+ halo) of 8 reduction channels goes through shared memory once - producer BatchNorm +
+//   LeakyReLU and the zero padding applied while staging, the next chunk's global loads issued before this chunk's
+//   math - and every thread keeps a 4-pixel x 8-channel register block: 12 FMAs per shared-memory instruction
+//   (128-bit input reads, 128-bit broadcast weight reads), 288 FMAs per reduction channel and thread.
+//   DGRAD: the same loop over dy with the weights read transposed and flipped (d x = dy * W^T_flipped), no bias,
+//   no statistics, optional accumulation.
+//   grid (ceil(W/32) * ceil(H/TR), ceil(Cout/16), N), TR * 16 threads. Measured (B200, ncu, netG at 896 px): 23 % (forward) /
+//   34 % (data gradient) of the FP32 FMA rate on the layers it serves, against ~12 % for the direct kernels; used only
+//   where 16-row tiles fill the GPU twice over (with fewer CTAs the per-chunk staging latency is exposed and the direct
+//   kernels win: 13.5 us against 103 us on the 224 px layers). netG forward + backward, 2 calls: 448 px 5.21 -> 5.02 ms,
+//   896 px 19.1 -> 17.4 ms; 224 px unchanged. What still limits it: ~40 % of its instructions are the index arithmetic of
+//   the staging loops (profiles/ANALYSIS_r2.md).
+// -------------------------------------------------------------------------------------------------
+template <int K, int TR, bool DGRAD>
+__global__ void __launch_bounds__(TR * 16, TR == 8 ? 4 : 2)
+conv_tiled_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, const float* __restrict__ Wt, int w_cout, int w_cin,
+                  const float* __restrict__ bias, int Cout, float* __restrict__ y, int accumulate, float* __restrict__ stats_part,
+                  BnFin fin) {
+    pdl_sync();
+    constexpr int NT = TR * 16, KK = K * K, PAD = (K - 1) / 2, CI_C = 8, CO_T = 16;
+    constexpr int IR = TR + K - 1, IC = 32 + K - 1, ICP = 36;          // staged rows / columns, padded row stride (16-byte rows)
+    constexpr int NE = (CI_C * IR * IC + NT - 1) / NT;                 // staged elements per thread and chunk
+    constexpr int NWARP = NT / 32, WPG = NWARP / 2;                    // warps per output-channel group
+    __shared__ __align__(16) float s_in[CI_C][IR][ICP];
+    __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
+    __shared__ float red[NWARP][8];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int q = tid % (TR * 8), cg = tid / (TR * 8);
+    const int r = q / 8, xq = q % 8;
+    const int tiles_x = (W + 31) / 32;
+    const int ty0 = (blockIdx.x / tiles_x) * TR, tx0 = (blockIdx.x % tiles_x) * 32;
+    const int co0 = blockIdx.y * CO_T, n = blockIdx.z;
+    const size_t plane = (size_t)H * W;
+    const float* xn = x + (size_t)n * Cin * plane;
+
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+
+    // global -> registers of one chunk's input tile (raw values + validity mask: nothing waits for the loads here),
+    // registers -> shared memory one chunk later (producer BatchNorm + LeakyReLU applied, padding zeroed)
+    float pre[NE];
+    unsigned pre_ok = 0;
+    auto fetch = [&](int c0) {
+        pre_ok = 0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int idx = tid + e * NT;
+            const int c = idx / (IR * IC), rem = idx % (IR * IC);
+            const int iy = ty0 - PAD + rem / IC, ix = tx0 - PAD + rem % IC;
+            const bool ok = idx < CI_C * IR * IC && c0 + c < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W;
+            pre[e] = ok ? xn[(size_t)(c0 + c) * plane + (size_t)iy * W + ix] : 0.f;
+            pre_ok |= ok ? (1u << e) : 0u;
+        }
+    };
+    auto stash = [&](int c0) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int idx = tid + e * NT;
+            if (idx < CI_C * IR * IC) {
+                const int c = idx / (IR * IC), rem = idx % (IR * IC);
+                float v = pre[e];
+                if (!DGRAD && tf.k && ((pre_ok >> e) & 1u)) {
+                    const float4 k4 = __ldg(tf.k + c0 + c);
+                    v = fmaf(k4.z, v, k4.w);
+                    if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
+                }
+                s_in[c][rem / IC][rem % IC] = v;
+            }
+        }
+    };
+
+    fetch(0);
+    for (int c0 = 0; c0 < Cin; c0 += CI_C) {
+        stash(c0);
+        for (int idx = tid; idx < CI_C * KK * CO_T; idx += NT) {
+            const int co = idx % CO_T, kk = (idx / CO_T) % KK, ci = idx / (CO_T * KK);
+            float w = 0.f;
+            if (c0 + ci < Cin && co0 + co < Cout) {
+                if (DGRAD) w = __ldg(Wt + ((size_t)(c0 + ci) * w_cin + co0 + co) * KK + (KK - 1 - kk));   // transposed, flipped
+                else w = __ldg(Wt + ((size_t)(co0 + co) * w_cin + c0 + ci) * KK + kk);
+            }
+            s_w[ci][kk][co] = w;
+        }
+        __syncthreads();
+        if (c0 + CI_C < Cin) fetch(c0 + CI_C);     // in flight while this chunk's FMAs run
+#pragma unroll 1
+        for (int ci = 0; ci < CI_C; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const float* row = &s_in[ci][r + ky][xq * 4];
+                float in[4 + K - 1];
+                const float4 a = *reinterpret_cast<const float4*>(row);
+                in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
+                if (K == 3) {
+                    const float2 b = *reinterpret_cast<const float2*>(row + 4);
+                    in[4] = b.x; in[4 + K - 2] = b.y;
+                }
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ci][ky * K + kx][cg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ci][ky * K + kx][cg * 8 + 4]);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[p + kx], w[j], acc[p][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int oy = ty0 + r, ox0 = tx0 + xq * 4;
+    const bool rowok = oy < H;
+    if (DGRAD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = co0 + cg * 8 + j;
+            if (co < Cout && rowok) {
+                float* o = y + ((size_t)(n * Cout + co) * H + oy) * W + ox0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (ox0 + p < W) o[p] = accumulate ? o[p] + acc[p][j] : acc[p][j];
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int co = co0 + cg * 8 + j;
+        const float b = co < Cout ? __ldg(bias + co) : 0.f;
+        float* o = y + ((size_t)(n * Cout + min(co, Cout - 1)) * H + min(oy, H - 1)) * W + ox0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            acc[p][j] += b;
+            if (co < Cout && rowok && ox0 + p < W) o[p] = acc[p][j];
+        }
+    }
+    if (stats_part) {
+        // per-tile (count, mean, M2) of each output channel over the tile's valid pixels: two block reductions, centred
+        const int lane = tid & 31, w = tid >> 5;
+        const float cnt = (float)(min(TR, H - ty0) * min(32, W - tx0));
+        float mean[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float sv = 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) sv += (rowok && ox0 + p < W) ? acc[p][j] : 0.f;
+            sv = warp_sum(sv);
+            if (lane == 0) red[w][j] = sv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float sv = 0.f;
+#pragma unroll
+            for (int u = 0; u < WPG; ++u) sv += red[cg * WPG + u][j];
+            mean[j] = sv / cnt;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float sv = 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float d = acc[p][j] - mean[j];
+                sv += (rowok && ox0 + p < W) ? d * d : 0.f;
+            }
+            sv = warp_sum(sv);
+            if (lane == 0) red[w][j] = sv;
+        }
+        __syncthreads();
+        const int part = blockIdx.z * gridDim.x + blockIdx.x, nparts = gridDim.x * gridDim.z;
+        if (q == 0) {       // one thread per output-channel group
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int co = co0 + cg * 8 + j;
+                if (co < Cout) {
+                    float m2 = 0.f;
+#pragma unroll
+                    for (int u = 0; u < WPG; ++u) m2 += red[cg * WPG + u][j];
+                    float* o = stats_part + ((size_t)part * Cout + co) * 3;
+                    o[0] = cnt; o[1] = mean[j]; o[2] = m2;
+                }
+            }
+        }
+        __syncthreads();    // both groups' partials are written before the ticket of this tile is drawn
+        if (fin.konst) bn_finish_if_last(stats_part, nparts, Cout, co0, CO_T, blockIdx.y, nparts, fin, &s_flag);
+    }
+}
+
+// the tiled kernel serves stride-1 K = 1 / 3 layers with enough pixels per image to be throughput-bound
+static inline bool use_tiled(int K, int S, int H, int W) {
+    static int on = -1;     // SPLICE_B200_GEN_TILED=0: every layer on the direct kernels (A/B cross-check of the two conv paths)
+    if (on < 0) {
+        const char* v = getenv("SPLICE_B200_GEN_TILED");
+        on = (v && v[0] == '0') ? 0 : 1;
+    }
+    return on && S == 1 && (K == 1 || K == 3) && H * W >= 2500 && W >= 24;
+}
+// ... and only when 16-row tiles fill the GPU twice over: with fewer CTAs the per-chunk staging latency of a CTA is exposed
+// (measured: 103 us against 13.5 us of the direct kernel for the 224 px layers)
+static inline bool tiled_fills(int N, int Cout, int H, int W) { return (long long)ceil_div(W, 32) * ceil_div(H, 16) * ceil_div(Cout, 16) * N >= 2 * 148; }
+template <bool DGRAD>
+static int launch_conv_tiled(int K, const float* x, int N, int Cin, int H, int W, InTf tf, const float* Wt, int w_cout, int w_cin,
+                             const float* bias, int Cout, float* y, int accumulate, float* stats_part, BnFin fin, cudaStream_t st) {
+    dim3 grid(ceil_div(W, 32) * ceil_div(H, 16), ceil_div(Cout, 16), N);
+    if (K == 3) SPLICE_CHECK_CUDA(launch_pdl(conv_tiled_kernel<3, 16, DGRAD>, grid, dim3(256), 0, st, x, Cin, H, W, tf, Wt, w_cout, w_cin, bias, Cout, y, accumulate, stats_part, fin));
+    else SPLICE_CHECK_CUDA(launch_pdl(conv_tiled_kernel<1, 16, DGRAD>, grid, dim3(256), 0, st, x, Cin, H, W, tf, Wt, w_cout, w_cin, bias, Cout, y, accumulate, stats_part, fin));
+    SPLICE_LAUNCH_CHECK();
+    return SPLICE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // host: launch helpers
 // -------------------------------------------------------------------------------------------------
 static constexpr int TARGET_BLOCKS = 296;          // two CTAs per SM on 148 SMs
@@ -788,6 +1010,9 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
                            const float* bias, int Cout, float* y, int Ho, int Wo, int sigmoid, const BnOut* bn, float* stats_part,
                            float* split_part, cudaStream_t st) {
     const int P = N * Ho * Wo;
+    if (bn && !sigmoid && Hin == Ho && Win == Wo && use_tiled(K, S, Ho, Wo) && tiled_fills(N, Cout, Ho, Wo))
+        return launch_conv_tiled<false>(K, x, N, Cin, Ho, Wo, tf, Wt, Cout, Cin, bias, Cout, y, 0, stats_part,
+                                        BnFin{bn->gamma, bn->beta, bn->konst, bn->bstat, bn->counter, 1e-5f}, st);
     int ct, sk;
     pick_tiling(P, Cout, Cin, (size_t)N * Cout * Ho * Wo, &ct, &sk);
     if (!bn) sk = 1;   // the final conv has no BatchNorm epilogue to fold the split reduction into
@@ -819,6 +1044,9 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
 static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int Ho, int Wo, const float* Wt, int Cin, float* dX,
                              int Hin, int Win, int accumulate, float* split_part, cudaStream_t st) {
     const int P = N * Hin * Win;
+    if (Hin == Ho && Win == Wo && use_tiled(K, S, Hin, Win) && tiled_fills(N, Cin, Hin, Win))
+        return launch_conv_tiled<true>(K, dy, N, Cout, Hin, Win, InTf{nullptr, 0}, Wt, Cout, Cin, nullptr, Cin, dX, accumulate, nullptr,
+                                       BnFin{nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f}, st);
     int ct, sk;
     const size_t total = (size_t)N * Cin * Hin * Win;
     pick_tiling(P, Cin, Cout, total, &ct, &sk);
@@ -838,6 +1066,30 @@ static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int
         SPLICE_CHECK_CUDA(launch_pdl(sum_partials_kernel, dim3(blocks), dim3(256), 0, st, (const float*)split_part, sk, total, dX, accumulate));
         SPLICE_LAUNCH_CHECK();
     }
+    return SPLICE_OK;
+}
+
+// test hook (capi: splice_gen_debug_conv): ONE stride-1 convolution (or its data gradient) on either kernel family, without
+// producer transform or statistics, so that the tiled and the direct kernels can be checked against a reference separately
+int gen_debug_conv(const float* x, int N, int Cin, int H, int W, const float* Wt, int Cout, int K, const float* bias, float* y,
+                   int dgrad, int tiled, cudaStream_t st) {
+    SPLICE_REQUIRE(K == 1 || K == 3, "gen_debug_conv: K must be 1 or 3");
+    const InTf none{nullptr, 0};
+    const BnFin nofin{nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f};
+    if (!dgrad) {   // y[N,Cout,H,W] = conv(x[N,Cin,H,W], Wt[Cout,Cin,K,K]) + bias
+        if (tiled) return launch_conv_tiled<false>(K, x, N, Cin, H, W, none, Wt, Cout, Cin, bias, Cout, y, 0, nullptr, nofin, st);
+        dim3 grid(ceil_div(N * H * W, CONV_THREADS), ceil_div(Cout, 16), 1);
+        if (K == 3) conv_fwd_kernel<3, 1, 16><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, H, W, none, Wt, bias, Cout, y, H, W, 0, nullptr, 1, nofin);
+        else conv_fwd_kernel<1, 1, 16><<<grid, CONV_THREADS, 0, st>>>(x, N, Cin, H, W, none, Wt, bias, Cout, y, H, W, 0, nullptr, 1, nofin);
+        SPLICE_LAUNCH_CHECK();
+        return SPLICE_OK;
+    }
+    // y[N,Cin,H,W] = d x given x = dy[N,Cout,H,W]
+    if (tiled) return launch_conv_tiled<true>(K, x, N, Cout, H, W, none, Wt, Cout, Cin, nullptr, Cin, y, 0, nullptr, nofin, st);
+    dim3 grid(ceil_div(N * H * W, CONV_THREADS), ceil_div(Cin, 16), 1);
+    if (K == 3) conv_dgrad_kernel<3, 1, 16><<<grid, CONV_THREADS, 0, st>>>(x, N, Cout, H, W, Wt, Cin, y, H, W, 0, 1);
+    else conv_dgrad_kernel<1, 1, 16><<<grid, CONV_THREADS, 0, st>>>(x, N, Cout, H, W, Wt, Cin, y, H, W, 0, 1);
+    SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }
 

@@ -22,6 +22,9 @@ struct GenPointers {
     long long* num_batches_tracked[GEN_BN];
 };
 
+int gen_debug_conv(const float* x, int N, int Cin, int H, int W, const float* Wt, int Cout, int K, const float* bias, float* y,
+                   int dgrad, int tiled, cudaStream_t st);
+
 class GenEngine {
 public:
     GenEngine();

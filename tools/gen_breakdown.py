@@ -12,8 +12,10 @@ cfg = make_cfg("dino_vitb8")
 torch.manual_seed(0)
 model = Model(cfg)
 net = model.netG
-A = synth_image(1000, 224, 8)[None].cuda()
-B = synth_image(1001, 224, 16)[None, :, :217, :217].contiguous().cuda()
+SIDE = int(sys.argv[1]) if len(sys.argv) > 1 else 224
+A = synth_image(1000, SIDE, 8)[None].cuda()
+B = synth_image(1001, SIDE, 16)[None, :, :SIDE - 7, :SIDE - 7].contiguous().cuda()
+print("generator input side", SIDE)
 
 
 def timeit(fn, reps=50):
