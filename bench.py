@@ -58,12 +58,16 @@ def vit_tokens(w: dict) -> int:
 
 def vit_gflop_per_step(w: dict) -> float:
     """Algorithmic ViT work of a steady-state step: per crop 4 distinct forwards + 2 dgrad-only
-    backward sequences; F(t) = 12(24tD^2 + 4t^2D) + 6(t-1)Dp^2, B(t) = 12(24tD^2 + 8t^2D) + 6(t-1)Dp^2."""
+    backward sequences; F(t) = 12(24tD^2 + 4t^2D) + 6(t-1)Dp^2, B(t) = 12(24tD^2 + 8t^2D) + 6(t-1)Dp^2 (983.2 GFLOP at
+    configs[1]). Two of the forwards (A_global, y_global) and one backward (y_global) are read only through their
+    layer-11 keys: they stop after the last layer's qkv projection, which removes that layer's attention + proj + MLP
+    (4t^2D + 18tD^2 forward, 8t^2D + 18tD^2 backward) from what the result needs (counted once implemented)."""
     p, D = VIT_ARCH[w["model"]]
     t = vit_tokens(w)
     F = 12 * (24 * t * D * D + 4 * t * t * D) + 6 * (t - 1) * D * p * p
     B = 12 * (24 * t * D * D + 8 * t * t * D) + 6 * (t - 1) * D * p * p
-    return w["n_crops"] * (4 * F + 2 * B) / 1e9
+    cutF, cutB = 4 * t * t * D + 18 * t * D * D, 8 * t * t * D + 18 * t * D * D
+    return w["n_crops"] * (4 * F + 2 * B - 2 * cutF - cutB) / 1e9
 
 
 def workload_string(w: dict) -> str:

@@ -122,6 +122,10 @@ typedef struct SpliceVitForwardArgs {
     int gemm_impl;         /* 0 = tcgen05 */
     int pre_normalized;    /* 1 = images are already ImageNet-normalised (VitExtractor API), skip (x-mean)/std */
     int use_graph;         /* 1 = the caller reuses the same output buffers every call: capture + replay a CUDA graph */
+    int n_full;            /* > 0: only the first n_full images need the last block's OUTPUT (cls32 rows 0..n_full-1); the others
+                            * are "keys-only" (ref: calculate_global_ssim_loss / calculate_global_id_loss, util/losses.py:74-83,96-105,
+                            * read nothing past block 11's qkv) and stop after the last layer's qkv projection, forward and
+                            * backward. 0 = every image runs the full depth, -1 = none does (all keys-only). Ignored when block32_all is requested. */
 } SpliceVitForwardArgs;
 SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* args, void* stream);
 
@@ -134,6 +138,13 @@ typedef struct SpliceVitBackwardArgs {
     const SpliceImage* grads;  /* host array, n_grad entries; data = fp32 [3,h,w] out (NULL entry = skip) */
     int gemm_impl;
     int use_graph;             /* 1 = dkeys32 / dcls32 are the same buffers every call: CUDA graph replay */
+    /* gradients w.r.t. the all-layer taps of the forward (qkv32_all / block32_all), for callers that differentiate through
+     * VitExtractor.get_feature_from_input / get_qkv_feature_from_input / get_keys_from_input at ANY layer (ref: inversion.py:33-39,
+     * args.layer 0..11). Host arrays of `depth` device pointers, entries NULL where no gradient flows; the arrays may be NULL.
+     * dblock32_layers[l]: fp32 [n_grad*t, D] = d loss / d (block l output); dqkv32_layers[l]: fp32 [n_grad*t, 3D]. Layers above the
+     * highest one that receives a gradient are skipped. Not graph-replayed. */
+    const void* const* dblock32_layers;
+    const void* const* dqkv32_layers;
 } SpliceVitBackwardArgs;
 SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* args, void* stream);
 

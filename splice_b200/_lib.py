@@ -73,6 +73,7 @@ class SpliceVitForwardArgs(C.Structure):
         ("gemm_impl", c_int),
         ("pre_normalized", c_int),
         ("use_graph", c_int),
+        ("n_full", c_int),
     ]
 
 
@@ -83,6 +84,8 @@ class SpliceVitBackwardArgs(C.Structure):
         ("grads", C.POINTER(SpliceImage)),
         ("gemm_impl", c_int),
         ("use_graph", c_int),
+        ("dblock32_layers", C.POINTER(c_void_p)),
+        ("dqkv32_layers", C.POINTER(c_void_p)),
     ]
 
 

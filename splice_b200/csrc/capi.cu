@@ -132,7 +132,7 @@ SPLICE_API int splice_vit_forward(void* ctx, const SpliceVitForwardArgs* a, void
     for (int i = 0; i < a->n_images; ++i) imgs[i] = ImageRef{(const float*)a->images[i].data, a->images[i].h, a->images[i].w};
     VitForwardArgs v;
     v.images = imgs; v.n_images = a->n_images; v.out_h = a->out_h; v.out_w = a->out_w; v.pos = (const float*)a->pos;
-    v.n_grad = a->n_grad; v.slot = a->slot; v.keys32 = (float*)a->keys32; v.cls32 = (float*)a->cls32;
+    v.n_grad = a->n_grad; v.n_full = a->n_full; v.slot = a->slot; v.keys32 = (float*)a->keys32; v.cls32 = (float*)a->cls32;
     v.qkv32_all = (float*)a->qkv32_all; v.block32_all = (float*)a->block32_all; v.gemm_impl = a->gemm_impl;
     v.pre_normalized = a->pre_normalized != 0;
     v.use_graph = a->use_graph != 0;
@@ -148,7 +148,9 @@ SPLICE_API int splice_vit_backward(void* ctx, const SpliceVitBackwardArgs* a, vo
     for (int i = 0; i < n; ++i) g[i] = ImageGradRef{(float*)a->grads[i].data, a->grads[i].h, a->grads[i].w};
     VitBackwardArgs v;
     v.slot = a->slot; v.dkeys32 = (const float*)a->dkeys32; v.dcls32 = (const float*)a->dcls32; v.gemm_impl = a->gemm_impl;
-    v.use_graph = a->use_graph != 0;
+    v.use_graph = a->use_graph != 0 && !a->dblock32_layers && !a->dqkv32_layers;
+    v.dblock32_layers = reinterpret_cast<const float* const*>(a->dblock32_layers);
+    v.dqkv32_layers = reinterpret_cast<const float* const*>(a->dqkv32_layers);
     v.grads = g;
     return e->backward(v, (cudaStream_t)stream);
 }

@@ -778,7 +778,6 @@ conv_tiled_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, c
     pdl_sync();
     constexpr int NT = TR * 16, KK = K * K, PAD = (K - 1) / 2, CI_C = 8, CO_T = 16;
     constexpr int IR = TR + K - 1, IC = 32 + K - 1, ICP = 36;          // staged rows / columns, padded row stride (16-byte rows)
-    constexpr int NE = (CI_C * IR * IC + NT - 1) / NT;                 // staged elements per thread and chunk
     constexpr int NWARP = NT / 32, WPG = NWARP / 2;                    // warps per output-channel group
     __shared__ __align__(16) float s_in[CI_C][IR][ICP];
     __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
@@ -800,34 +799,64 @@ conv_tiled_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, c
         for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
 
     // global -> registers of one chunk's input tile (raw values + validity mask: nothing waits for the loads here),
-    // registers -> shared memory one chunk later (producer BatchNorm + LeakyReLU applied, padding zeroed)
-    float pre[NE];
-    unsigned pre_ok = 0;
+    // registers -> shared memory one chunk later (producer BatchNorm + LeakyReLU applied, padding zeroed).
+    // A warp owns whole tile rows (row id = warp + 8 i: channel c = id / IR, tile row rr = id % IR, advanced without
+    // divisions), lane l the column l of the 32 main columns; the K - 1 halo columns of all rows are spread over the first
+    // threads. Staging costs ~8 instructions per element this way (the flat index -> (c, row, col) form cost ~25).
+    constexpr int NR = CI_C * IR / NWARP;              // rows per warp and chunk (18 for K = 3, 16 for K = 1)
+    constexpr int NH = (K - 1) * CI_C * IR;            // halo elements per chunk
+    constexpr int NHT = (NH + NT - 1) / NT;            // ... per thread
+    static_assert(CI_C * IR % NWARP == 0 && NWARP <= IR, "row ownership");
+    const int lane = tid & 31, wid = tid >> 5;
+    const int ix_main = tx0 - PAD + lane;
+    const bool col_ok = ix_main >= 0 && ix_main < W;
+    float pre[NR], preh[NHT > 0 ? NHT : 1];
+    unsigned pre_ok = 0, preh_ok = 0;
     auto fetch = [&](int c0) {
-        pre_ok = 0;
+        pre_ok = 0; preh_ok = 0;
+        int c = 0, rr = wid;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int idx = tid + e * NT;
-            const int c = idx / (IR * IC), rem = idx % (IR * IC);
-            const int iy = ty0 - PAD + rem / IC, ix = tx0 - PAD + rem % IC;
-            const bool ok = idx < CI_C * IR * IC && c0 + c < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W;
-            pre[e] = ok ? xn[(size_t)(c0 + c) * plane + (size_t)iy * W + ix] : 0.f;
-            pre_ok |= ok ? (1u << e) : 0u;
+        for (int i = 0; i < NR; ++i) {
+            const int iy = ty0 - PAD + rr;
+            const bool ok = col_ok && c0 + c < Cin && iy >= 0 && iy < H;
+            pre[i] = ok ? xn[(size_t)(c0 + c) * plane + (size_t)iy * W + ix_main] : 0.f;
+            pre_ok |= ok ? (1u << i) : 0u;
+            rr += NWARP;
+            if (rr >= IR) { rr -= IR; ++c; }
+        }
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) {
+            const int e = tid + h * NT;
+            const int row = e / (K - 1 > 0 ? K - 1 : 1), side = e % (K - 1 > 0 ? K - 1 : 1);
+            const int c2 = row / IR, iy = ty0 - PAD + row % IR, ix = tx0 - PAD + 32 + side;
+            const bool ok = e < NH && c0 + c2 < Cin && iy >= 0 && iy < H && ix < W;
+            preh[h] = ok ? xn[(size_t)(c0 + c2) * plane + (size_t)iy * W + ix] : 0.f;
+            preh_ok |= ok ? (1u << h) : 0u;
         }
     };
+    auto transform = [&](float v, int c) {
+        if (!DGRAD && tf.k) {
+            const float4 k4 = __ldg(tf.k + c);
+            v = fmaf(k4.z, v, k4.w);
+            if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
+        }
+        return v;
+    };
     auto stash = [&](int c0) {
+        int c = 0, rr = wid;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int idx = tid + e * NT;
-            if (idx < CI_C * IR * IC) {
-                const int c = idx / (IR * IC), rem = idx % (IR * IC);
-                float v = pre[e];
-                if (!DGRAD && tf.k && ((pre_ok >> e) & 1u)) {
-                    const float4 k4 = __ldg(tf.k + c0 + c);
-                    v = fmaf(k4.z, v, k4.w);
-                    if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
-                }
-                s_in[c][rem / IC][rem % IC] = v;
+        for (int i = 0; i < NR; ++i) {
+            s_in[c][rr][lane] = ((pre_ok >> i) & 1u) ? transform(pre[i], c0 + c) : 0.f;
+            rr += NWARP;
+            if (rr >= IR) { rr -= IR; ++c; }
+        }
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) {
+            const int e = tid + h * NT;
+            if (e < NH) {
+                const int row = e / (K - 1 > 0 ? K - 1 : 1), side = e % (K - 1 > 0 ? K - 1 : 1);
+                const int c2 = row / IR;
+                s_in[c2][row % IR][32 + side] = ((preh_ok >> h) & 1u) ? transform(preh[h], c0 + c2) : 0.f;
             }
         }
     };
@@ -901,7 +930,7 @@ conv_tiled_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, c
     }
     if (stats_part) {
         // per-tile (count, mean, M2) of each output channel over the tile's valid pixels: two block reductions, centred
-        const int lane = tid & 31, w = tid >> 5;
+        const int w = wid;
         const float cnt = (float)(min(TR, H - ty0) * min(32, W - tx0));
         float mean[8];
 #pragma unroll

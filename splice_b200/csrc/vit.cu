@@ -269,6 +269,8 @@ int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
     Slot& s = slots_[a.slot];
     RC(configure(s, S, t, a.n_grad));
     s.gh = gh; s.gw = gw; s.oh = a.out_h; s.ow = a.out_w; s.pre_normalized = a.pre_normalized;
+    SPLICE_REQUIRE(a.n_full >= -1 && a.n_full <= S, "vit_forward: n_full out of range");
+    s.n_full = a.block32_all ? S : (a.n_full > 0 ? a.n_full : (a.n_full < 0 ? 0 : S));
     s.imgs.assign(a.images, a.images + S);
     const float* pos = a.pos ? a.pos : pos_;
 
@@ -277,7 +279,7 @@ int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
                           !a.pre_normalized, stream));
     if (prof_on_ || !a.use_graph) return forward_body(a, s, S, t, pos, stream);
     KeyHasher k;
-    k.add((uint64_t)1).add((uint64_t)a.slot).add((uint64_t)S).add((uint64_t)t).add((uint64_t)a.n_grad).add(s.pool).add(pos)
+    k.add((uint64_t)1).add((uint64_t)a.slot).add((uint64_t)S).add((uint64_t)t).add((uint64_t)a.n_grad).add((uint64_t)s.n_full).add(s.pool).add(pos)
         .add(a.keys32).add(a.cls32).add(a.qkv32_all).add(a.block32_all).add((uint64_t)a.gemm_impl);
     return graphs_.run(k.h, stream, [&](cudaStream_t st) { return forward_body(a, s, S, t, pos, st); });
 }
@@ -306,32 +308,35 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
             if (l == depth - 1 && a.keys32) { ep.slice32 = a.keys32; ep.slice_c0 = D; ep.slice_c1 = 2 * D; ep.ldslice = D; }
             PROF(PROF_GEMM, GEMM_FLOPS(M, 3 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.qkv_w, D, M, 3 * D, D, ep, a.gemm_impl, 0, stream));
         }
-        PROF(PROF_ATTN_FWD, 4.0 * S * (double)t * t * D, 0.0, attention_fwd(s.qkv[l], s.o[l], s.lse[l], S, t, D, H, stream));
+        // the rest of the LAST layer only serves the block output ([CLS] row): keys-only sequences (the trailing S - n_full) stop here
+        const int Sf = (l == depth - 1) ? s.n_full : S, Mf = Sf * t;
+        if (Sf == 0) continue;
+        PROF(PROF_ATTN_FWD, 4.0 * Sf * (double)t * t * D, 0.0, attention_fwd(s.qkv[l], s.o[l], s.lse[l], Sf, t, D, H, stream));
         {
             GemmEpilogue ep;
             ep.b_const = 1;
             ep.c32 = s.x1[l]; ep.ldc32 = D; ep.bias = L.proj_b; ep.residual = s.x0[l]; ep.ldr = D;
-            PROF(PROF_GEMM, GEMM_FLOPS(M, D, D), 0.0, gemm_bf16_tn(s.o[l], D, L.proj_w, D, M, D, D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(Mf, D, D), 0.0, gemm_bf16_tn(s.o[l], D, L.proj_w, D, Mf, D, D, ep, a.gemm_impl, 0, stream));
         }
-        PROF(PROF_ROWWISE, 0.0, 6.0 * M * D, layernorm_fwd(s.x1[l], L.ln2_g, L.ln2_b, s.a16, s.st2[l], M, D, d_.ln_eps, stream));
+        PROF(PROF_ROWWISE, 0.0, 6.0 * Mf * D, layernorm_fwd(s.x1[l], L.ln2_g, L.ln2_b, s.a16, s.st2[l], Mf, D, d_.ln_eps, stream));
         {
             GemmEpilogue ep;
             ep.b_const = 1;
             ep.c16 = s.h16; ep.ldc16 = 4 * D; ep.bias = L.fc1_b; ep.act = GEMM_ACT_GELU; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
-            PROF(PROF_GEMM, GEMM_FLOPS(M, 4 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.fc1_w, D, M, 4 * D, D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(Mf, 4 * D, D), 0.0, gemm_bf16_tn(s.a16, D, L.fc1_w, D, Mf, 4 * D, D, ep, a.gemm_impl, 0, stream));
         }
         {
             GemmEpilogue ep;
             ep.b_const = 1;
             ep.c32 = s.x0[l + 1]; ep.ldc32 = D; ep.bias = L.fc2_b; ep.residual = s.x1[l]; ep.ldr = D;
-            PROF(PROF_GEMM, GEMM_FLOPS(M, D, 4 * D), 0.0, gemm_bf16_tn(s.h16, 4 * D, L.fc2_w, 4 * D, M, D, 4 * D, ep, a.gemm_impl, 0, stream));
+            PROF(PROF_GEMM, GEMM_FLOPS(Mf, D, 4 * D), 0.0, gemm_bf16_tn(s.h16, 4 * D, L.fc2_w, 4 * D, Mf, D, 4 * D, ep, a.gemm_impl, 0, stream));
         }
         if (a.block32_all)
             SPLICE_CHECK_CUDA(cudaMemcpyAsync(a.block32_all + (size_t)l * M * D, s.x0[l + 1], (size_t)M * D * sizeof(float),
                                               cudaMemcpyDeviceToDevice, stream));
     }
-    if (a.cls32) {
-        SPLICE_CHECK_CUDA(launch_pdl(gather_cls_kernel, dim3(S), dim3(256), 0, stream, (const float*)s.x0[depth], a.cls32, t, D));
+    if (a.cls32 && s.n_full > 0) {
+        SPLICE_CHECK_CUDA(launch_pdl(gather_cls_kernel, dim3(s.n_full), dim3(256), 0, stream, (const float*)s.x0[depth], a.cls32, t, D));
         SPLICE_LAUNCH_CHECK();
     }
     return SPLICE_OK;
@@ -349,7 +354,7 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
         RC(backward_body(a, s, stream));
     } else {
         KeyHasher k;
-        k.add((uint64_t)2).add((uint64_t)a.slot).add((uint64_t)s.S).add((uint64_t)Sg).add((uint64_t)t).add(s.pool).add(a.dkeys32).add(a.dcls32)
+        k.add((uint64_t)2).add((uint64_t)a.slot).add((uint64_t)s.S).add((uint64_t)Sg).add((uint64_t)s.n_full).add((uint64_t)t).add(s.pool).add(a.dkeys32).add(a.dcls32)
             .add((uint64_t)a.gemm_impl);
         RC(graphs_.run(k.h, stream, [&](cudaStream_t st) { return backward_body(a, s, st); }));
     }
@@ -365,6 +370,16 @@ int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
 }
 
 
+// g += src (fp32 residual-stream gradient), g16 = bf16(g): a tap gradient entering the stream between two blocks
+__global__ void __launch_bounds__(256) add_stream_grad_kernel(float* __restrict__ g, bf16* __restrict__ g16, const float* __restrict__ src, size_t n) {
+    pdl_sync();
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float v = g[i] + src[i];
+        g[i] = v;
+        g16[i] = __float2bfloat16(v);
+    }
+}
+
 int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t stream) {
     const int p = d_.patch, D = d_.dim, H = d_.heads, depth = d_.depth, pp3 = 3 * p * p;
     const int t = s.t, Sg = s.n_grad, Mg = Sg * t;
@@ -379,34 +394,48 @@ int VitEngine::backward_body(const VitBackwardArgs& a, Slot& s, cudaStream_t str
     }
     for (int l = depth - 1; l >= 0; --l) {
         const LayerW& L = L_[l];
-        if (have_g) {
+        const float* dblock = a.dblock32_layers ? a.dblock32_layers[l] : nullptr;
+        const float* dqkv = a.dqkv32_layers ? a.dqkv32_layers[l] : nullptr;
+        if (dblock) {   // gradient w.r.t. block l's output (an all-layer tap): joins the residual-stream gradient here
+            const size_t n = (size_t)Mg * D;
+            const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+            SPLICE_CHECK_CUDA(launch_pdl(add_stream_grad_kernel, dim3(blocks), dim3(256), 0, stream, s.g, s.g16, dblock, n));
+            SPLICE_LAUNCH_CHECK();
+            have_g = true;
+        }
+        // last layer: only the first n_full sequences ran past the qkv projection (the others are keys-only)
+        const int Sb = (l == depth - 1 && s.n_full < Sg) ? s.n_full : Sg, Mb = Sb * t;
+        if (have_g && Sb > 0) {
             {   // d(gelu out) = g W2 ; d(pre) = . * gelu'(pre)
                 GemmEpilogue ep;
             ep.b_const = 1;
                 ep.c16 = s.dh16; ep.ldc16 = 4 * D; ep.act = GEMM_ACT_GELU_GRAD; ep.aux16 = s.hpre[l]; ep.ldaux = 4 * D;
-                PROF(PROF_GEMM, GEMM_FLOPS(Mg, 4 * D, D), 0.0, gemm_bf16_tn(s.g16, D, L.fc2_wT, D, Mg, 4 * D, D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mb, 4 * D, D), 0.0, gemm_bf16_tn(s.g16, D, L.fc2_wT, D, Mb, 4 * D, D, ep, a.gemm_impl, 0, stream));
             }
             {   // d(LN2 out) = d(pre) W1
                 GemmEpilogue ep;
             ep.b_const = 1;
                 ep.c32 = s.da; ep.ldc32 = D;
-                PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, 4 * D), 0.0, gemm_bf16_tn(s.dh16, 4 * D, L.fc1_wT, 4 * D, Mg, D, 4 * D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mb, D, 4 * D), 0.0, gemm_bf16_tn(s.dh16, 4 * D, L.fc1_wT, 4 * D, Mb, D, 4 * D, ep, a.gemm_impl, 0, stream));
             }
-            PROF(PROF_ROWWISE, 0.0, 18.0 * Mg * D, layernorm_bwd(s.da, s.x1[l], s.st2[l], L.ln2_g, s.g, s.g, s.g16, Mg, D, stream));
+            PROF(PROF_ROWWISE, 0.0, 18.0 * Mb * D, layernorm_bwd(s.da, s.x1[l], s.st2[l], L.ln2_g, s.g, s.g, s.g16, Mb, D, stream));
             {   // d(attn out) = g Wproj
                 GemmEpilogue ep;
             ep.b_const = 1;
                 ep.c16 = s.do16; ep.ldc16 = D;
-                PROF(PROF_GEMM, GEMM_FLOPS(Mg, D, D), 0.0, gemm_bf16_tn(s.g16, D, L.proj_wT, D, Mg, D, D, ep, a.gemm_impl, 0, stream));
+                PROF(PROF_GEMM, GEMM_FLOPS(Mb, D, D), 0.0, gemm_bf16_tn(s.g16, D, L.proj_wT, D, Mb, D, D, ep, a.gemm_impl, 0, stream));
             }
-            PROF(PROF_ATTN_BWD, 8.0 * Sg * (double)t * t * D, 0.0,
-                 attention_bwd(s.qkv[l], s.o[l], s.do16, s.lse[l], s.delta, s.dqkv16, Sg, t, D, H, stream));
+            PROF(PROF_ATTN_BWD, 8.0 * Sb * (double)t * t * D, 0.0,
+                 attention_bwd(s.qkv[l], s.o[l], s.do16, s.lse[l], s.delta, s.dqkv16, Sb, t, D, H, stream));
+            if (Mb < Mg)   // keys-only sequences: d(qkv) starts at zero
+                SPLICE_CHECK_CUDA(cudaMemsetAsync(s.dqkv16 + (size_t)Mb * 3 * D, 0, (size_t)(Mg - Mb) * 3 * D * sizeof(bf16), stream));
         } else {
             // nothing flows back from the block output (keys-only objective): d(qkv) starts at zero
             SPLICE_CHECK_CUDA(cudaMemsetAsync(s.dqkv16, 0, (size_t)Mg * 3 * D * sizeof(bf16), stream));
         }
         if (l == depth - 1 && a.dkeys32) RC(add_f32_into_bf16_cols(s.dqkv16, 3 * D, D, a.dkeys32, D, Mg, D, stream));
-        if (!have_g && !(l == depth - 1 && a.dkeys32)) continue;  // still all-zero
+        if (dqkv) RC(add_f32_into_bf16_cols(s.dqkv16, 3 * D, 0, dqkv, 3 * D, Mg, 3 * D, stream));
+        if (!have_g && !(l == depth - 1 && a.dkeys32) && !dqkv) continue;  // still all-zero
         {   // d(LN1 out) = d(qkv) Wqkv
             GemmEpilogue ep;
             ep.b_const = 1;

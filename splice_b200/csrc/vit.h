@@ -23,6 +23,7 @@ struct VitForwardArgs {
     int out_h = 0, out_w = 0;
     const float* pos = nullptr;       // [1 + gh*gw, D] or nullptr = native pos_embed
     int n_grad = 0;
+    int n_full = 0;                   // > 0: images beyond the first n_full stop after the last layer's qkv projection
     int slot = 0;
     float* keys32 = nullptr;          // [n_images*t, D]
     float* cls32 = nullptr;           // [n_images, D]
@@ -40,6 +41,8 @@ struct VitBackwardArgs {
     const ImageGradRef* grads = nullptr;  // n_grad entries
     int gemm_impl = 0;
     bool use_graph = false;
+    const float* const* dblock32_layers = nullptr;   // [depth] -> [n_grad*t, D] or null
+    const float* const* dqkv32_layers = nullptr;     // [depth] -> [n_grad*t, 3D] or null
 };
 
 enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN_FWD = 1, PROF_ATTN_BWD = 2, PROF_ROWWISE = 3, PROF_PREPROC = 4, PROF_NCAT = 5 };
@@ -68,7 +71,7 @@ private:
         const bf16 *qkv_w, *qkv_wT, *proj_w, *proj_wT, *fc1_w, *fc1_wT, *fc2_w, *fc2_wT;
     };
     struct Slot {
-        int S = 0, t = 0, gh = 0, gw = 0, n_grad = 0, oh = 0, ow = 0;
+        int S = 0, t = 0, gh = 0, gw = 0, n_grad = 0, oh = 0, ow = 0, n_full = 0;
         bool pos_custom = false, pre_normalized = false;
         std::vector<ImageRef> imgs;
         void* pool = nullptr;

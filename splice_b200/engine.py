@@ -126,11 +126,12 @@ class VitEngine:
     def forward(self, images: Sequence[torch.Tensor], out_hw: Tuple[int, int], n_grad: int = 0, slot: int = 0,
                 want_keys: bool = True, want_cls: bool = True, want_all_qkv: bool = False,
                 want_all_blocks: bool = False, pre_normalized: bool = False, use_graph: bool = False,
-                stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                stream: Optional[int] = None, n_full: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """images: fp32 CUDA tensors [3,h,w] in [0,1] (sizes may differ); all are resized to out_hw.
         `stream` (raw cudaStream_t, default: torch's current stream): passes in different slots may be in flight on
         different streams; the caller orders the streams (outputs are cached per slot, so no allocation happens here
-        after the first call).
+        after the first call). `n_full`: only the first n_full images need the last block's output ('cls'); the others
+        are keys-only and stop after the last layer's qkv projection (None = all images run the full depth).
         Returns {'keys': [S,t,D], 'cls': [S,D], 'qkv': [12,S,t,3D], 'block': [12,S,t,D]} (only the requested)."""
         S = len(images)
         oh, ow = out_hw
@@ -170,6 +171,7 @@ class VitEngine:
         a.gemm_impl = self.gemm_impl
         a.pre_normalized = 1 if pre_normalized else 0
         a.use_graph = 1 if use_graph else 0
+        a.n_full = 0 if n_full is None or n_full >= S else (-1 if n_full <= 0 else n_full)
         check(_lib.splice_vit_forward(self._ctx, C.byref(a), cur_stream() if stream is None else stream), "splice_vit_forward")
         self._slot_meta[slot] = {"shapes": [(im.shape[1], im.shape[2]) for im in keep[:n_grad]], "t": t, "keep": keep}
         return out
@@ -190,8 +192,10 @@ class VitEngine:
         return dk, dc
 
     def backward(self, slot: int, dkeys: Optional[torch.Tensor], dcls: Optional[torch.Tensor],
-                 use_graph: bool = False) -> List[torch.Tensor]:
-        """d(loss)/d(image) for the first n_grad images of the forward held in `slot`."""
+                 use_graph: bool = False, dblocks: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                 dqkvs: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[torch.Tensor]:
+        """d(loss)/d(image) for the first n_grad images of the forward held in `slot`. `dblocks` / `dqkvs`: per-layer
+        gradients w.r.t. the all-layer taps ([n_grad,t,D] / [n_grad,t,3D] or None), for differentiable VitExtractor calls."""
         meta = self._slot_meta[slot]
         n = len(meta["shapes"])
         grads = [torch.empty(3, h, w, device=self.device) for (h, w) in meta["shapes"]]
@@ -206,6 +210,23 @@ class VitEngine:
             assert dcls.dtype == torch.float32 and dcls.is_contiguous() and dcls.numel() == n * self.dim
         a.dkeys32, a.dcls32, a.grads, a.gemm_impl = ptr(dkeys), ptr(dcls), arr, self.gemm_impl
         a.use_graph = 1 if use_graph else 0
+        hold = []
+        for name, lst, width in (("dblock32_layers", dblocks, self.dim), ("dqkv32_layers", dqkvs, 3 * self.dim)):
+            if lst is None or all(g is None for g in lst):
+                continue
+            if len(lst) != DEPTH:
+                raise ValueError(f"{name}: one entry per layer ({DEPTH}) expected")
+            arr2 = (C.c_void_p * DEPTH)()
+            for i, g in enumerate(lst):
+                if g is None:
+                    continue
+                g = g.detach().to(torch.float32).contiguous()
+                if g.numel() != n * meta["t"] * width:
+                    raise ValueError(f"{name}[{i}] has {g.numel()} elements, expected {n * meta['t'] * width}")
+                hold.append(g)
+                arr2[i] = g.data_ptr()
+            setattr(a, name, arr2)
+            hold.append(arr2)
         check(_lib.splice_vit_backward(self._ctx, C.byref(a), cur_stream()), "splice_vit_backward")
         return grads
 

@@ -27,6 +27,38 @@ def attn_cosine_sim(x, eps=1e-08):
     return eng.keys_self_sim(x[0].detach().float().contiguous())[None]
 
 
+class _TapFn(torch.autograd.Function):
+    """All-layer taps of one image as an autograd node (ref: inversion.py:33-39 back-propagates through
+    get_feature_from_input / get_keys_from_input into the generator). Forward = one engine pass that keeps its activations
+    (slot 6); backward = the engine's dgrad-only pass started from whatever per-layer tap gradients arrive."""
+
+    @staticmethod
+    def forward(ctx, input_img, extractor, kind):
+        eng = extractor.engine
+        img = input_img[0]
+        res = eng.forward([img], (img.shape[1], img.shape[2]), n_grad=1, slot=_TapFn.SLOT, want_keys=False, want_cls=False,
+                          want_all_qkv=(kind == "qkv"), want_all_blocks=(kind == "block"), pre_normalized=True)
+        _TapFn.token += 1
+        ctx.eng, ctx.kind, ctx.token = eng, kind, _TapFn.token
+        ctx.set_materialize_grads(False)
+        return tuple(res[kind][i] for i in range(12))
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        if ctx.token != _TapFn.token:
+            raise RuntimeError("VitExtractor: another differentiable tap call replaced this pass's activations before "
+                               "backward() (one differentiable call may be alive at a time)")
+        if all(g is None for g in gouts):
+            return None, None, None
+        kw = {"dblocks": list(gouts)} if ctx.kind == "block" else {"dqkvs": list(gouts)}
+        g = ctx.eng.backward(_TapFn.SLOT, None, None, **kw)[0]
+        return g[None], None, None
+
+
+_TapFn.SLOT = 6
+_TapFn.token = 0
+
+
 class VitExtractor:
     BLOCK_KEY = 'block'
     ATTN_KEY = 'attn'
@@ -90,11 +122,26 @@ class VitExtractor:
         _, _, h, w = input_img.shape
         return self.engine.forward_normalized(input_img[0], **want)
 
+    @staticmethod
+    def _wants_grad(input_img) -> bool:
+        return torch.is_grad_enabled() and input_img.requires_grad
+
+    def _taps_with_grad(self, input_img, kind):
+        if input_img.dim() != 4 or input_img.shape[0] != 1:
+            raise ValueError("VitExtractor expects a [1,3,h,w] batch (ref extractor.py:143 requires batch 1)")
+        if input_img.dtype != torch.float32 or not input_img.is_contiguous():
+            input_img = input_img.float().contiguous()
+        return list(_TapFn.apply(input_img, self, kind))
+
     def get_feature_from_input(self, input_img):  # List([B, N, D])
+        if self._wants_grad(input_img):      # differentiable, like the reference's hooked module (inversion.py:35)
+            return self._taps_with_grad(input_img, "block")
         res = self._run(input_img, want_all_blocks=True)
         return [res["block"][i] for i in range(12)]
 
     def get_qkv_feature_from_input(self, input_img):
+        if self._wants_grad(input_img):
+            return self._taps_with_grad(input_img, "qkv")
         res = self._run(input_img, want_all_qkv=True)
         return [res["qkv"][i] for i in range(12)]
 
@@ -154,7 +201,7 @@ class VitExtractor:
 
     def get_keys_from_input(self, input_img, layer_num):
         """[H,t,dh] keys of `layer_num` (ref :153-156). Layer 11 is served by the engine's direct fp32 export."""
-        if layer_num in (11, -1):
+        if layer_num in (11, -1) and not self._wants_grad(input_img):
             res = self._run(input_img)
             t = res["keys"].shape[1]
             H = self.get_head_num()

@@ -83,6 +83,8 @@ class LossG(torch.nn.Module):
         self.engine: VitEngine = self.extractor.engine
         self.global_transform = GlobalTransform(self.engine, cfg['dino_global_patch_size'])
         self.overlap_targets = True     # targets' ViT pass on a side stream, in the shadow of the generator forward
+        self.keys_only_stop = True      # sequences only read through their layer-11 keys stop after the last qkv projection
+        self.run_ahead_max_pixels = 80_000   # generated images up to this size: the targets' pass may run ahead of the main stream
         self._side = None
         self._targets_consumed = None   # event: the loss kernels of the last forward() have read the targets' features
         self.lambdas = dict(
@@ -151,6 +153,11 @@ class LossG(torch.nn.Module):
         for name, kind, lam, gen, tgt in plan:
             for i in range(min(len(gen), len(tgt))):  # zip() semantics of the reference loops
                 pairs.append((TERM_ORDER.index(name), kind, lam, seq_of(gen, i, True), seq_of(tgt, i, False)))
+        # sequences read only through their layer-11 keys (ssim / identity terms: ref losses.py:74-83,96-105) stop after the
+        # last layer's qkv projection; those a [CLS] term reads (losses.py:85-94) run the full depth and go first in a pass
+        for _, kind, _, g, tg in pairs:
+            if kind == CLS:
+                g["full"] = tg["full"] = True
 
         # 2. one batched engine forward per ViT input size, generated (grad) sequences first
         groups: Dict[Tuple[int, int], List[dict]] = {}
@@ -160,8 +167,9 @@ class LossG(torch.nn.Module):
             raise NotImplementedError("more than 3 distinct ViT input sizes in one step")
         main = torch.cuda.current_stream()
         for g_idx, (hw, members) in enumerate(groups.items()):
-            members.sort(key=lambda s: not s["gen"])
+            members.sort(key=lambda s: (not s["gen"], not s.get("full", False)))
             n_grad = sum(1 for s in members if s["gen"])
+            n_full_of = (lambda part: sum(1 for s in part if s.get("full", False))) if self.keys_only_stop else (lambda part: None)
             slot = 2 * g_idx
             if self.overlap_targets and 0 < n_grad < len(members):
                 # The targets (A_global, B_global, A) do not depend on netG: their no-grad pass goes to a side stream
@@ -170,7 +178,12 @@ class LossG(torch.nn.Module):
                 gens, tgts = members[:n_grad], members[n_grad:]
                 side = self._side_stream()
                 ready = [getattr(s["batch"], "_splice_ready", None) for s in tgts]
-                if any(e is None for e in ready):
+                # Run-ahead only pays while the generator leaves SMs idle (224 px: its kernels are latency-bound). Once its
+                # conv kernels are throughput-bound, a persistent GEMM CTA (~200 KB of shared memory) parked on an SM
+                # leaves room for ONE conv CTA instead of several: measured 117 -> 65 it/s at 448 px and 48 -> 25 it/s on
+                # the 1200x900 pair with run-ahead on. Above the threshold the pass is ordered after the main stream.
+                big = max(s["img"].shape[1] * s["img"].shape[2] for s in gens) > self.run_ahead_max_pixels
+                if big or any(e is None for e in ready):
                     side.wait_stream(main)
                 else:
                     for e in {id(e): e for e in ready}.values():
@@ -181,13 +194,17 @@ class LossG(torch.nn.Module):
                         side.wait_event(self._targets_consumed)
                 for s in tgts:
                     s["batch"].record_stream(side)
-                ft = eng.forward([s["img"] for s in tgts], hw, n_grad=0, slot=slot + 1, use_graph=True, stream=side.cuda_stream)
-                fg = eng.forward([s["img"] for s in gens], hw, n_grad=n_grad, slot=slot, use_graph=True)
+                ft = eng.forward([s["img"] for s in tgts], hw, n_grad=0, slot=slot + 1, use_graph=True, stream=side.cuda_stream,
+                                 n_full=n_full_of(tgts))
+                fg = eng.forward([s["img"] for s in gens], hw, n_grad=n_grad, slot=slot, use_graph=True, n_full=n_full_of(gens))
                 main.wait_stream(side)
                 t = fg["keys"].shape[1]
                 parts = [(gens, fg), (tgts, ft)]
             else:
-                feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot, use_graph=True)
+                # one pass: full-depth sequences must be a PREFIX, so every sequence up to the last one a [CLS] term reads runs full
+                last_full = max([j for j, s in enumerate(members) if s.get("full", False)], default=-1)
+                feats = eng.forward([s["img"] for s in members], hw, n_grad=n_grad, slot=slot, use_graph=True,
+                                    n_full=(last_full + 1) if self.keys_only_stop else None)
                 t = feats["keys"].shape[1]
                 parts = [(members, feats)]
             dkeys, dcls = eng.grad_buffers(slot, n_grad, t) if n_grad else (None, None)

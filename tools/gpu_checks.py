@@ -992,6 +992,55 @@ def extractor_attn_taps():
 
 
 @check
+def extractor_differentiable_taps():
+    """VitExtractor as the reference's inversion.py uses it (inversion.py:33-52): the feature of ANY layer - the [CLS] row of a
+    block output or a layer's keys - as a differentiable function of the input image, MSE against a target feature,
+    back-propagated to the pixels through torch's Resize + Normalize. Against the oracle's autograd (fp32): loss 5e-3 rel
+    (1e-2 for a single [CLS] row: 384 numbers after 12 bf16 layers, measured 5.7e-3 at layer 11), d loss / d image 3e-2
+    rel-L2 (one bf16 sequence)."""
+    import torch
+    from torchvision import transforms as T
+
+    dino_vit, R = _oracle_on_gpu()
+    from splice_b200.models.extractor import VitExtractor
+
+    name = "dino_vits16"
+    vsd = {k: v.detach() for k, v in dino_vit.build(name).cuda().state_dict().items()}
+    ext = VitExtractor(name, "cuda", state_dict=vsd)
+    H = ext.get_head_num()
+    pre = T.Compose([T.Resize(224), T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    target_img = torch.rand(1, 3, 200, 260, device="cuda", generator=g)
+    rows = []
+    for feature, layer in (("cls", 11), ("keys", 11), ("cls", 4), ("keys", 7), ("keys", 0)):
+        def feat_product(x):
+            if feature == "cls":
+                return ext.get_feature_from_input(pre(x))[layer][:, 0, :]
+            return ext.get_keys_from_input(pre(x), layer)
+
+        def feat_oracle(x):
+            taps = R.vit_taps(vsd, pre(x))
+            if feature == "cls":
+                return taps["block"][layer][:, 0, :]
+            return R.keys_from_qkv(taps["qkv"][layer], H)
+
+        with torch.no_grad():
+            ref_p, ref_o = feat_product(target_img), feat_oracle(target_img)
+        x0 = torch.rand(1, 3, 200, 260, device="cuda", generator=g)        # Resize(224) -> 224 x 291: non-square ViT input
+        xp, xo = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        lp = torch.nn.functional.mse_loss(feat_product(xp), ref_p)
+        lp.backward()
+        lo = torch.nn.functional.mse_loss(feat_oracle(xo), ref_o)
+        lo.backward()
+        r = {"feature": feature, "layer": layer, "loss": lp.item(), "loss_ref": lo.item(),
+             "loss_rel": abs(lp.item() - lo.item()) / max(abs(lo.item()), 1e-12), "dx_rel": _rel(xp.grad, xo.grad),
+             "grad_norm": xo.grad.norm().item()}
+        r["ok"] = r["loss_rel"] < (1e-2 if feature == "cls" else 5e-3) and r["dx_rel"] < 3e-2 and r["grad_norm"] > 0
+        rows.append(r)
+    return rows
+
+
+@check
 def lossg_overlap_targets():
     """The targets' ViT pass on a side stream (overlapping the generator forward) must give the same objective and the
     same gradients as the single batched pass on one stream: the rows of a batched GEMM / LayerNorm / attention do not

@@ -13,7 +13,7 @@ from splice_b200.util.util import get_optimizer
 from splice_b200 import _lib
 
 name = sys.argv[1] if len(sys.argv) > 1 else "dino_vitb8"
-side = 224
+side = int(sys.argv[2]) if len(sys.argv) > 2 else 224
 cfg = make_cfg(name)
 torch.manual_seed(0)
 model = Model(cfg)
