@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 template <int K, int S>
 constexpr int wgrad_smem_floats() {
     constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-    constexpr int a = 8 * IH * (IW + 1) + 16 * TH * (TW + 1), b = 8 * 32 * (4 * K * K + 4);
+    constexpr int a = 8 * IH * (IW + 1) + 16 * (TH * (TW + 1) + 1), b = 8 * 32 * (4 * K * K + 4);
     return a > b ? a : b;
 }
 template <int K, int S>
@@ -614,7 +614,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     constexpr int SX = CI_T * IH * IWP;
     extern __shared__ float smem[];   // wgrad_smem_floats<K, S>() floats (K=3, S=2 needs 52.8 KB: opt-in dynamic)
     float (*s_x)[IH][IWP] = reinterpret_cast<float (*)[IH][IWP]>(smem);
-    float (*s_dy)[TH][TW + 1] = reinterpret_cast<float (*)[TH][TW + 1]>(smem + SX);
+    // dy tile [16][TH][TW + 1] with a channel stride of 265 floats: the four output-channel quads a warp reads for one pixel
+    // (channels 0-3 / 4-7 / 8-11 / 12-15) then sit in different banks (a stride of 264 put all four in one bank: a 4-way
+    // conflict on 4 of the 13 shared-memory loads per pixel of a kernel that is bound by exactly those loads)
+    constexpr int SDY = TH * (TW + 1) + 1;
+    float* s_dy = smem + SX;
     const int co0 = (blockIdx.y / ((Cin + CI_T - 1) / CI_T)) * CO_T;
     const int ci0 = (blockIdx.y % ((Cin + CI_T - 1) / CI_T)) * CI_T;
     const int g = threadIdx.x >> 5, w = threadIdx.x & 31;   // pixel group, weight thread
@@ -644,14 +648,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
             const int oy = ty0 + r, ox = tx0 + q;
             float v = 0.f;
             if (co0 + c < Cout && oy < Ho && ox < Wo) v = dy[((size_t)(n * Cout + co0 + c) * Ho + oy) * Wo + ox];
-            s_dy[c][r][q] = v;
+            s_dy[c * SDY + r * (TW + 1) + q] = v;
         }
         __syncthreads();
         for (int p = g; p < TH * TW; p += 8) {
             const int py = p / TW, px = p % TW;
             float d[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = s_dy[cos + j][py][px];
+            for (int j = 0; j < 4; ++j) d[j] = s_dy[(cos + j) * SDY + py * (TW + 1) + px];
 #pragma unroll
             for (int j = 0; j < 4; ++j) bacc[j] += d[j];
 #pragma unroll

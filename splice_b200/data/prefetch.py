@@ -39,7 +39,7 @@ class PrefetchedSamples:
                 for k, v in sample.items():
                     if torch.is_tensor(v):
                         v = v.clone() if k == 'step' else v.contiguous()
-                        if self.pin and k != 'step':
+                        if self.pin and k != 'step' and not v.is_cuda:     # device-side feeds hand over CUDA tensors
                             v = v.pin_memory()
                     out[k] = v
                 while not self._stop.is_set():
