@@ -27,6 +27,10 @@ NVCC_FLAGS = [
     "-I", str(PKG_DIR.parent / "include"),
     "-I", str(CSRC),
 ]
+# SPLICE_B200_CROSSCHECK=1: also build the cross-check kernels (mma.sync attention, one-tile-per-CTA GEMM, the 96-wide and
+# thread-block-cluster GEMM shapes) that A/B tools select through SPLICE_B200_ATTN / impl / bn_hint. Not in the product library.
+if os.environ.get("SPLICE_B200_CROSSCHECK", "0") == "1":
+    NVCC_FLAGS.append("-DSPLICE_B200_CROSSCHECK")
 
 
 def _nvcc() -> str:
@@ -78,7 +82,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or not LIB_PATH.exists() or force:
-        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs)]
+        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,6 +21,7 @@
 namespace splice {
 
 static constexpr int HD = 64;       // head dim
+#ifdef SPLICE_B200_CROSSCHECK   // the mma.sync kernels are cross-check code: built only into the test library (build.py)
 static constexpr int TQ = 64;       // rows per CTA tile
 static constexpr int TK = 64;       // columns (keys / queries) per inner tile
 static constexpr int TILE_BYTES = 64 * 64 * 2;
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restric
     store_acc_bf16(dqkv + (size_t)s * t * ld + 2 * D + h * HD, ld, row_lo, t, dv, 1.f, 1.f, lane);
 }
 
+#endif  // SPLICE_B200_CROSSCHECK
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -465,11 +467,16 @@ int attention_fwd(const bf16* qkv, bf16* o, float* lse, int S, int t, int D, int
     int rc = check_dims(S, t, D, H);
     if (rc) return rc;
     if (!(attn_mode() & 1)) return attention_fwd_tc(qkv, o, lse, S, t, D, H, stream);
+#ifndef SPLICE_B200_CROSSCHECK
+    set_error("attention: the mma.sync cross-check kernels are not in this build (SPLICE_B200_CROSSCHECK=1 python -m splice_b200.build)");
+    return SPLICE_ERR_UNSUPPORTED;
+#else
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     dim3 grid(ceil_div(t, TQ), H, S);
     SPLICE_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(128), 0, stream, qkv, o, lse, t, D, scale_log2));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
+#endif
 }
 
 int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float* lse, float* delta, bf16* dqkv, int S, int t,
@@ -477,6 +484,10 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
     int rc = check_dims(S, t, D, H);
     if (rc) return rc;
     if (!(attn_mode() & 2)) return attention_bwd_tc(qkv, o, dout, lse, delta, dqkv, S, t, D, H, stream);
+#ifndef SPLICE_B200_CROSSCHECK
+    set_error("attention: the mma.sync cross-check kernels are not in this build (SPLICE_B200_CROSSCHECK=1 python -m splice_b200.build)");
+    return SPLICE_ERR_UNSUPPORTED;
+#else
     const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
     dim3 grid(ceil_div(t, TQ), H, S);
     SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(128), 0, stream, qkv, o, dout, lse, delta, dqkv, t, D, scale, scale_log2));
@@ -484,6 +495,7 @@ int attention_bwd(const bf16* qkv, const bf16* o, const bf16* dout, const float*
     SPLICE_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(128), 0, stream, qkv, dout, lse, delta, dqkv, t, D, scale, scale_log2));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
+#endif
 }
 
 }  // namespace splice

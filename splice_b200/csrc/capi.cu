@@ -209,6 +209,7 @@ int gram(const bf16* a, const bf16* b, int t, int tp, int D, float* S, int impl,
 
 SPLICE_API int splice_loss_ssim(void* ctx, const void* keys_x, const void* keys_a, int t, float coef, void* dkeys_x,
                                 void* loss, int gemm_impl, void* stream) {
+    NvtxRange nvtx("splice_loss_ssim");
     SPLICE_REQUIRE(ctx && keys_x && keys_a && loss && t > 0, "splice_loss_ssim: bad argument");
     VitEngine* e = static_cast<VitEngine*>(ctx);
     cudaStream_t st = (cudaStream_t)stream;
@@ -348,6 +349,7 @@ SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, 
 SPLICE_API int splice_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                                 const int* numel, int n_tensors, int step, float lr, float beta1, float beta2, float eps,
                                 void* stream) {
+    NvtxRange nvtx("splice_adam_step");
     SPLICE_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && n_tensors > 0 && step >= 1, "splice_adam_step: bad argument");
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);

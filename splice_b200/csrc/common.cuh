@@ -57,6 +57,20 @@ void count_launch(int n = 1);  // every kernel launch of this library is counted
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// NVTX range around a host-side enqueue (the passes of a step show up as named ranges in Nsight Systems /
+// ncu --nvtx). Header-only NVTX3: a no-op unless a profiler injects itself; SPLICE_B200_NVTX=0 compiles it out.
+#if !defined(SPLICE_B200_NVTX) || SPLICE_B200_NVTX
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#else
+struct NvtxRange { explicit NvtxRange(const char*) {} };
+#endif
+
 // Programmatic dependent launch (PDL): kernels of one dependency chain are launched with the
 // programmaticStreamSerialization attribute, so the next kernel's CTAs are scheduled (and run their prologue:
 // barrier init, TMEM allocation, descriptor prefetch, index math) while the previous kernel drains, instead of

@@ -563,11 +563,16 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
         return SPLICE_OK;
     }
     if (impl == GEMM_IMPL_TCGEN05_TILE) {   // first-generation one-tile-per-CTA kernel (kept for A/B comparison)
+#ifdef SPLICE_B200_CROSSCHECK
         switch (bn_hint) {
             case 64:  return launch_tcgen05<64, 4>(A, lda, B, ldb, M, N, K, ep, stream);
             case 256: return launch_tcgen05<256, 4>(A, lda, B, ldb, M, N, K, ep, stream);
             default:  return launch_tcgen05<128, 3>(A, lda, B, ldb, M, N, K, ep, stream);
         }
+#else
+        set_error("gemm: the one-tile-per-CTA kernel is cross-check code, not in this build (SPLICE_B200_CROSSCHECK=1 python -m splice_b200.build)");
+        return SPLICE_ERR_UNSUPPORTED;
+#endif
     }
     SPLICE_REQUIRE(impl == GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
 
@@ -585,15 +590,22 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
     if (cm == 0 || cn == 0) default_cluster(bn, M, N, &cm, &cn);
 #define SPLICE_GEMM_CASE(BN_, ST_, CM_, CN_) \
     if (bn == BN_ && cm == CM_ && cn == CN_) return launch_persistent<BN_, ST_, CM_, CN_>(A, lda, B, ldb, M, N, K, ep, stream)
+    // the product build holds the shapes the dispatch above selects (one CTA per tile column, no cluster); the 96-wide tile
+    // and the thread-block-cluster / TMA-multicast variants were measured no faster (profiles/ANALYSIS_r1.md) and are
+    // cross-check code: SPLICE_B200_CROSSCHECK=1 python -m splice_b200.build
     SPLICE_GEMM_CASE(64, 6, 1, 1);
+    SPLICE_GEMM_CASE(128, 5, 1, 1);
+    SPLICE_GEMM_CASE(256, 4, 1, 1);
+#ifdef SPLICE_B200_CROSSCHECK
     SPLICE_GEMM_CASE(96, 6, 1, 1);
-    SPLICE_GEMM_CASE(128, 5, 1, 1); SPLICE_GEMM_CASE(128, 5, 2, 1); SPLICE_GEMM_CASE(128, 5, 1, 2);
+    SPLICE_GEMM_CASE(128, 5, 2, 1); SPLICE_GEMM_CASE(128, 5, 1, 2);
     SPLICE_GEMM_CASE(128, 5, 2, 2); SPLICE_GEMM_CASE(128, 5, 4, 1); SPLICE_GEMM_CASE(128, 5, 4, 2);
-    SPLICE_GEMM_CASE(256, 4, 1, 1); SPLICE_GEMM_CASE(256, 4, 2, 1); SPLICE_GEMM_CASE(256, 4, 1, 2);
+    SPLICE_GEMM_CASE(256, 4, 2, 1); SPLICE_GEMM_CASE(256, 4, 1, 2);
     SPLICE_GEMM_CASE(256, 4, 2, 2); SPLICE_GEMM_CASE(256, 4, 4, 1); SPLICE_GEMM_CASE(256, 4, 4, 2);
+#endif
 #undef SPLICE_GEMM_CASE
-    set_error("gemm: unsupported tile/cluster BN=%d cluster %dx%d", bn, cm, cn);
-    return SPLICE_ERR_ARG;
+    set_error("gemm: tile/cluster BN=%d cluster %dx%d is not in this build (cross-check shapes: SPLICE_B200_CROSSCHECK=1 python -m splice_b200.build)", bn, cm, cn);
+    return SPLICE_ERR_UNSUPPORTED;
 }
 
 }  // namespace splice

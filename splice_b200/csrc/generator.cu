@@ -1245,6 +1245,7 @@ int GenEngine::configure(Slot& s, int N, int H, int W) {
 
 int GenEngine::forward(const GenPointers& p, const float* x, int N, int H, int W, float* out, int slot, bool keep,
                        bool update_running, cudaStream_t st) {
+    NvtxRange nvtx("splice_gen_forward");
     SPLICE_REQUIRE(slot >= 0 && slot < GEN_SLOTS, "generator: slot out of range");
     SPLICE_REQUIRE(x && out && N > 0 && H > 0 && W > 0, "generator: bad input");
     Slot& s = slots_[slot];
@@ -1362,6 +1363,7 @@ int GenEngine::forward_body(const GenPointers& p, Slot& s, cudaStream_t st) {
 }
 
 int GenEngine::backward(const GenPointers& p, const float* dout, int slot, bool accumulate, cudaStream_t st) {
+    NvtxRange nvtx("splice_gen_backward");
     SPLICE_REQUIRE(slot >= 0 && slot < GEN_SLOTS, "generator: slot out of range");
     Slot& s = slots_[slot];
     SPLICE_REQUIRE(s.pool && s.valid, "generator backward: slot %d holds no kept forward pass", slot);

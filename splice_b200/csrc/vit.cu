@@ -257,6 +257,7 @@ int VitEngine::profile_read(ProfTotals* out, int n) {
     } while (0)
 
 int VitEngine::forward(const VitForwardArgs& a, cudaStream_t stream) {
+    NvtxRange nvtx("splice_vit_forward");
     SPLICE_REQUIRE(a.images && a.n_images > 0, "vit_forward: no images");
     SPLICE_REQUIRE(a.slot >= 0 && a.slot < VIT_SLOTS, "vit_forward: slot must be in [0,%d)", VIT_SLOTS);
     SPLICE_REQUIRE(a.n_grad >= 0 && a.n_grad <= a.n_images, "vit_forward: n_grad out of range");
@@ -343,6 +344,7 @@ int VitEngine::forward_body(const VitForwardArgs& a, Slot& s, int S, int t, cons
 }
 
 int VitEngine::backward(const VitBackwardArgs& a, cudaStream_t stream) {
+    NvtxRange nvtx("splice_vit_backward");
     SPLICE_REQUIRE(a.slot >= 0 && a.slot < VIT_SLOTS, "vit_backward: slot must be in [0,%d)", VIT_SLOTS);
     Slot& s = slots_[a.slot];
     SPLICE_REQUIRE(s.pool && s.n_grad > 0, "vit_backward: slot %d holds no forward pass with n_grad > 0", a.slot);

@@ -111,7 +111,7 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     if log is not None:
         log.flush()
     if imglog is not None:
-        imglog.flush()
+        imglog.close()
     if feed is not None:
         feed.close()
     return model
