@@ -18,14 +18,24 @@ class SpliceError(RuntimeError):
 
 
 def _load() -> C.CDLL:
-    if not LIB_PATH.exists():
-        if os.environ.get("SPLICE_B200_AUTOBUILD", "1") == "1":
-            from . import build as _build
+    """Loads the library after checking that it was built from THIS tree: build.py writes a hash of the sources, headers
+    and flags next to the .so (it travels with it to the GPU box); on a mismatch the library is rebuilt when nvcc is
+    available (SPLICE_B200_AUTOBUILD=0 disables that) and refused otherwise - a stale library would turn an ABI or
+    struct-layout change into memory corruption."""
+    from . import build as _build
 
-            _build.build()
-        if not LIB_PATH.exists():
+    stamp = _build.STAMP_PATH.read_text().strip() if _build.STAMP_PATH.exists() else None
+    fresh = LIB_PATH.exists() and stamp == _build.tree_stamp()
+    if not fresh:
+        if os.environ.get("SPLICE_B200_AUTOBUILD", "1") == "1":
+            try:
+                _build.build()
+                fresh = True
+            except Exception as e:  # noqa: BLE001
+                raise ImportError(f"{LIB_PATH} is missing or stale and could not be rebuilt: {e}") from e
+        if not fresh:
             raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m splice_b200.build` "
+                f"{LIB_PATH} is missing or was built from different sources: build it with `python -m splice_b200.build` "
                 "(or __graft_entry__.build()); splice_b200 has no fallback path"
             )
     return C.CDLL(str(LIB_PATH))
@@ -172,6 +182,14 @@ EXPORTS = [
     "splice_accumulate", "splice_gen_update_running", "splice_gen_debug_conv",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
+
+
+ABI_VERSION = 100
+if splice_version() != ABI_VERSION:
+    raise ImportError(f"{LIB_PATH} reports ABI version {splice_version()}, this package binds version {ABI_VERSION}")
+_missing = [name for name in EXPORTS if not hasattr(lib, name)]
+if _missing:
+    raise ImportError(f"{LIB_PATH} does not export {_missing}")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -48,6 +48,21 @@ def _stamp(src: Path, headers: list[Path]) -> str:
     return h.hexdigest()
 
 
+STAMP_PATH = PKG_DIR / "libsplice_b200.so.stamp"
+
+
+def tree_stamp() -> str:
+    """Hash of everything the library is built from (sources, headers, flags): written next to the .so by build(), compared
+    by _lib at import so that a stale library is never loaded silently."""
+    h = hashlib.sha1()
+    files = sorted(CSRC.glob("*.cu")) + sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((PKG_DIR.parent / "include").glob("*.h")))
+    for p in files:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(verbose: bool = False, force: bool = False) -> Path:
     """Compile every .cu for sm_100a and link the shared library. Returns the .so path."""
     OBJ_DIR.mkdir(exist_ok=True)
@@ -88,6 +103,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    STAMP_PATH.write_text(tree_stamp())
     return LIB_PATH
 
 

@@ -66,13 +66,20 @@ def skip(
             fill_level(nxt, i + 1, c_down)
 
     # the default-argument network (the only one the optimisation loop builds, models/networks.py:57) runs on the
-    # native sm_100a generator engine; any other configuration keeps the plain module-by-module evaluation
+    # native sm_100a generator engine. Any other configuration is refused: evaluating it module by module with torch /
+    # cuDNN would be a silent second backend (north_star: no multi-backend dispatch). inversion.py's variant (6 scales,
+    # 7x7 / 5x5 filters, reflection padding) keeps using the reference's own models/unet.
     is_default = (num_input_channels == 3 and num_output_channels == 3 and list(num_channels_down) == [16, 32, 64, 128, 128]
                   and list(num_channels_up) == [16, 32, 64, 128, 128] and list(num_channels_skip) == [4, 4, 4, 4, 4]
                   and k_down == [3] * 5 and k_up == [3] * 5 and filter_skip_size == 1 and need_sigmoid and need_bias
                   and pad == 'zero' and up_modes == ['bilinear'] * 5 and down_modes == ['stride'] * 5
                   and act_fun == 'LeakyReLU' and need1x1_up)
-    model = NativeSkip() if is_default else nn.Sequential()
+    if not is_default:
+        raise NotImplementedError("splice_b200's generator engine implements the default-argument skip() network only "
+                                  "(5 scales [16,32,64,128,128], 3x3 / 1x1 filters, zero padding, bilinear up-sampling, "
+                                  "strided down-sampling, LeakyReLU, sigmoid); use the reference's models/unet for other "
+                                  "configurations")
+    model = NativeSkip()
     fill_level(model, 0, num_input_channels)
     model.add(conv(num_channels_up[0], num_output_channels, 1, bias=need_bias, pad=pad))
     if need_sigmoid:

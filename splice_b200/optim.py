@@ -69,7 +69,13 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             # steady state: same parameters, same (flat-buffer) gradient addresses, one common step count -> the ctypes
             # pointer tables of the previous step are reused and the per-parameter bookkeeping is one integer
-            key = tuple(p.grad.data_ptr() for p in ps)
+            # (the key also covers the parameter and state addresses at both ends of the list: `.to()` / state surgery
+            # that moves them while the flat gradient stays put must not leave stale pointers in the tables)
+            def _ends(p):
+                st = self.state.get(p, {})
+                return (p.data_ptr(), st['exp_avg'].data_ptr() if 'exp_avg' in st else 0,
+                        st['exp_avg_sq'].data_ptr() if 'exp_avg_sq' in st else 0)
+            key = tuple(p.grad.data_ptr() for p in ps) + _ends(ps[0]) + _ends(ps[-1])
             cached = self._fast.get(gi)
             if cached is not None and cached['key'] == key and all(p.grad.is_contiguous() for p in ps):
                 cached['step'] += 1
@@ -105,6 +111,7 @@ class FusedAdam(torch.optim.Optimizer):
                                             float(group['betas'][0]), float(group['betas'][1]), float(group['eps']),
                                             cur_stream()), "splice_adam_step")
                 if len(by_step) == 1 and len(sel) == len(ps) and all(g is p.grad for g, p in zip(grads, sel)):
+                    key = tuple(p.grad.data_ptr() for p in ps) + _ends(ps[0]) + _ends(ps[-1])   # state exists now
                     self._fast[gi] = {'key': key, 'tables': tables, 'n': n, 'step': step, 'params': list(sel)}
         return loss
 

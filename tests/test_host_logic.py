@@ -71,6 +71,12 @@ def test_out_of_scope_generator_options_raise():
         skip(downsample_mode="lanczos2")
     with pytest.raises(NotImplementedError):
         skip(act_fun="Swish")
+    # ... and so does every other non-default configuration (no silent torch-module evaluation), e.g. inversion.py:21-25
+    with pytest.raises(NotImplementedError):
+        skip(32, 3, num_channels_down=[16, 32, 64, 128, 128, 128], num_channels_up=[16, 32, 64, 128, 128, 128],
+             num_channels_skip=[4, 4, 4, 4, 4, 4], filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3])
+    with pytest.raises(NotImplementedError):
+        skip(need_sigmoid=False)
 
 
 def test_scheduler_and_optimizer_factories():
