@@ -59,7 +59,7 @@ def tree_stamp() -> str:
     for p in files:
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())   # include paths differ between machines
     return h.hexdigest()
 
 
