@@ -598,10 +598,20 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 
 // partial weight / bias gradients over a strided subset of the spatial tiles.
 // part layout: [gridDim.x][Cout*Cin*K*K + Cout]  (bias gradient partials at the end)
+//   A CTA owns 16 output channels x 8 input channels (x K*K taps) and walks 8 x 32 pixel tiles: x tile (+ halo, producer
+//   BatchNorm + LeakyReLU applied while staging) and dy tile in shared memory. A warp visits every 8th pixel of the tile;
+//   its 32 threads are the 4 output-channel quads x 8 input channels, each with 4 x K*K accumulators: per pixel ONE
+//   128-bit load of dy (the tile is stored pixel-major, channels contiguous, rows padded to 20 floats so that both the
+//   transposing store and the load are conflict-free) + K*K loads of x for 4*K*K FMAs.
+//   History: round 1 kept the dy tile channel-major - 4 scalar loads per pixel, all four quads in ONE bank (4-way
+//   conflict): 25 shared-memory wavefronts per 36 FMAs, FMA pipe 34-38 % active. Padding the channel stride (13
+//   wavefronts): 896 px backward 11.4 -> 10.6 ms. An 8-channel register block (72 accumulators, 11 wavefronts per 72
+//   FMAs) measured SLOWER (11.3 ms): 122 registers halve the resident warps and the loads of a pixel are exposed.
+static constexpr int DYP = 20;   // padded row of the pixel-major dy tile: 16 channels + 4
 template <int K, int S>
 constexpr int wgrad_smem_floats() {
     constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-    constexpr int a = 8 * IH * (IW + 1) + 16 * (TH * (TW + 1) + 1), b = 8 * 32 * (4 * K * K + 4);
+    constexpr int a = 8 * IH * (IW + 1) + 4 + TH * TW * DYP, b = 8 * 32 * (4 * K * K + 4);
     return a > b ? a : b;
 }
 template <int K, int S>
@@ -612,13 +622,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     constexpr int CO_T = 16, CI_T = 8, PAD = (K - 1) / 2, KK = K * K;
     constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K, IWP = IW + 1;
     constexpr int SX = CI_T * IH * IWP;
-    extern __shared__ float smem[];   // wgrad_smem_floats<K, S>() floats (K=3, S=2 needs 52.8 KB: opt-in dynamic)
+    extern __shared__ __align__(16) float smem[];   // wgrad_smem_floats<K, S>() floats (opt-in dynamic: > 48 KB for K=3, S=2)
     float (*s_x)[IH][IWP] = reinterpret_cast<float (*)[IH][IWP]>(smem);
-    // dy tile [16][TH][TW + 1] with a channel stride of 265 floats: the four output-channel quads a warp reads for one pixel
-    // (channels 0-3 / 4-7 / 8-11 / 12-15) then sit in different banks (a stride of 264 put all four in one bank: a 4-way
-    // conflict on 4 of the 13 shared-memory loads per pixel of a kernel that is bound by exactly those loads)
-    constexpr int SDY = TH * (TW + 1) + 1;
-    float* s_dy = smem + SX;
+    float* s_dy = smem + ((SX + 3) & ~3);           // [TH*TW][DYP], 16-byte aligned rows
     const int co0 = (blockIdx.y / ((Cin + CI_T - 1) / CI_T)) * CO_T;
     const int ci0 = (blockIdx.y % ((Cin + CI_T - 1) / CI_T)) * CI_T;
     const int g = threadIdx.x >> 5, w = threadIdx.x & 31;   // pixel group, weight thread
@@ -643,19 +649,26 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
                 v = apply_tf(tf, ci0 + c, x[((size_t)(n * Cin + ci0 + c) * Hin + iy) * Win + ix]);
             s_x[c][r][q] = v;
         }
-        for (int idx = threadIdx.x; idx < CO_T * TH * TW; idx += 256) {
-            const int c = idx / (TH * TW), r = (idx / TW) % TH, q = idx % TW;
-            const int oy = ty0 + r, ox = tx0 + q;
-            float v = 0.f;
-            if (co0 + c < Cout && oy < Ho && ox < Wo) v = dy[((size_t)(n * Cout + co0 + c) * Ho + oy) * Wo + ox];
-            s_dy[c * SDY + r * (TW + 1) + q] = v;
+        // dy tile, transposed to pixel-major: one item = (pixel, 4 consecutive channels) -> 4 coalesced global loads, 1 STS.128
+        for (int idx = threadIdx.x; idx < TH * TW * (CO_T / 4); idx += 256) {
+            const int pix = idx % (TH * TW), c4 = (idx / (TH * TW)) * 4;
+            const int oy = ty0 + pix / TW, ox = tx0 + pix % TW;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oy < Ho && ox < Wo) {
+                const float* src = dy + ((size_t)(n * Cout + co0 + c4) * Ho + oy) * Wo + ox;
+                const size_t cs = (size_t)Ho * Wo;
+                if (co0 + c4 + 0 < Cout) v.x = src[0];
+                if (co0 + c4 + 1 < Cout) v.y = src[cs];
+                if (co0 + c4 + 2 < Cout) v.z = src[2 * cs];
+                if (co0 + c4 + 3 < Cout) v.w = src[3 * cs];
+            }
+            *reinterpret_cast<float4*>(s_dy + pix * DYP + c4) = v;
         }
         __syncthreads();
         for (int p = g; p < TH * TW; p += 8) {
             const int py = p / TW, px = p % TW;
-            float d[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = s_dy[(cos + j) * SDY + py * (TW + 1) + px];
+            const float4 d4 = *reinterpret_cast<const float4*>(s_dy + p * DYP + cos);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) bacc[j] += d[j];
 #pragma unroll
@@ -683,17 +696,17 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     float* out = part + (size_t)blockIdx.x * (nW + Cout);
     for (int idx = threadIdx.x; idx < 32 * RS; idx += 256) {
         const int ww = idx / RS, e = idx % RS;
-        float s = 0.f;
+        float sv = 0.f;
 #pragma unroll
-        for (int gg = 0; gg < 8; ++gg) s += red[(gg * 32 + ww) * RS + e];
+        for (int gg = 0; gg < 8; ++gg) sv += red[(gg * 32 + ww) * RS + e];
         const int wcos = (ww / CI_T) * 4, wci = ww % CI_T;
         if (e < 4 * KK) {
             const int j = e / KK, kk = e % KK;
             const int co = co0 + wcos + j, c = ci0 + wci;
-            if (co < Cout && c < Cin) out[((size_t)co * Cin + c) * KK + kk] = s;
+            if (co < Cout && c < Cin) out[((size_t)co * Cin + c) * KK + kk] = sv;
         } else if (ci0 == 0 && wci == 0) {
             const int co = co0 + wcos + (e - 4 * KK);
-            if (co < Cout) out[nW + co] = s;
+            if (co < Cout) out[nW + co] = sv;
         }
     }
 }

@@ -44,7 +44,8 @@ if fullres:
 else:
     variants = (("prefetch=4, async log (default)", {}), ("prefetch=0 (inline sampling)", {"prefetch": 0}),
                 ("prefetch=0, log_sync (reference loop semantics)", {"prefetch": 0, "log_sync": True}),
-                ("prefetch=4, image logging off", {"log_images_freq": 10 ** 9}))
+                ("prefetch=4, image logging off", {"log_images_freq": 10 ** 9}),
+                ("device-side feed (device_aug), prefetch=4", {"device_aug": True}))
 for label, ov in variants:
     ov = {"dino_model_name": "dino_vitb8", "n_epochs": n, "seed": 0, **ov}
     train_model(str(root), overrides={**ov, "n_epochs": 100 if fullres else 160})          # graph capture for every crop shape
