@@ -31,6 +31,13 @@ class PrefetchedSamples:
 
     def _run(self):
         try:
+            # this thread's torch CPU ops (ToTensor, crops) single-threaded: a second OpenMP team that spins after every
+            # parallel region costs the main loop more than the few hundred microseconds it saves here (OpenMP's thread
+            # count is a per-thread setting: the main thread keeps its own)
+            try:
+                torch.set_num_threads(1)
+            except Exception:  # noqa: BLE001
+                pass
             for _ in range(self.n):
                 if self._stop.is_set():
                     return

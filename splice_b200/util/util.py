@@ -169,6 +169,12 @@ class AsyncImageLog:
         self._threading = threading
 
     def _run(self):
+        # torch CPU ops issued from a new thread bring up that thread's own OpenMP team, whose workers spin after every
+        # parallel region and starve the (Python-bound) main loop: this thread runs them single-threaded
+        try:
+            torch.set_num_threads(1)
+        except Exception:  # noqa: BLE001
+            pass
         while True:
             item = self._q.get()
             if item is None:
