@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
 #pragma unroll
     for (int i = 0; i < LN_MAX_V4; ++i)
         if (i < nv) {
-            const float4 d = dyr[lane + i * 32], xv = xr[lane + i * 32], g = __ldg(g4 + lane + i * 32);
+            const float4 d = dyr[lane + i * 32], xv = xr[lane + i * 32];
+            const float4 g = gamma ? __ldg(g4 + lane + i * 32) : make_float4(1.f, 1.f, 1.f, 1.f);   // null: gamma folded into the weights
             dg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
             xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
             s1 += dg[i].x + dg[i].y + dg[i].z + dg[i].w;
@@ -113,11 +114,25 @@ __global__ void cast_kernel(const float4* __restrict__ src, uint2* __restrict__ 
     }
 }
 
+// x16 / stat_part (optional): the bf16 copy of the row and its per-32-column (sum, centred sum of squares) partials, what
+// the GEMM epilogues write for every other residual-stream row when LayerNorm is folded into the GEMMs (gemm.h)
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int t,
-                                int D) {
+                                int D, bf16* __restrict__ x16, float2* __restrict__ stat_part) {
     pdl_sync();
     const int s = blockIdx.x;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) x[(size_t)s * t * D + c] = cls[c] + pos[c];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int c0 = warp * 32; c0 < D; c0 += nwarp * 32) {     // D is a multiple of 128
+        const int c = c0 + lane;
+        const float v = cls[c] + pos[c];
+        x[(size_t)s * t * D + c] = v;
+        if (x16) x16[(size_t)s * t * D + c] = __float2bfloat16(v);
+        if (stat_part) {
+            const float sum = warp_sum(v);
+            const float d = v - sum * (1.f / 32.f);
+            const float m2 = warp_sum(d * d);
+            if (lane == 0) stat_part[(size_t)s * t * (D / 32) + (c0 >> 5)] = make_float2(sum, m2);
+        }
+    }
 }
 
 __global__ void add_cols_kernel(bf16* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int lds, int rows,
@@ -163,8 +178,9 @@ int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream)
     return SPLICE_OK;
 }
 
-int write_cls_rows(float* x, const float* cls, const float* pos, int S, int t, int D, cudaStream_t stream) {
-    SPLICE_CHECK_CUDA(launch_pdl(cls_rows_kernel, dim3(S), dim3(256), 0, stream, x, cls, pos, t, D));
+int write_cls_rows(float* x, const float* cls, const float* pos, int S, int t, int D, cudaStream_t stream, bf16* x16,
+                   float2* stat_part) {
+    SPLICE_CHECK_CUDA(launch_pdl(cls_rows_kernel, dim3(S), dim3(256), 0, stream, x, cls, pos, t, D, x16, stat_part));
     SPLICE_LAUNCH_CHECK();
     return SPLICE_OK;
 }

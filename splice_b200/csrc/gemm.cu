@@ -113,6 +113,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
         const int quad = warp & 3;
         const int row = m0 + quad * 32 + lane;
+        const GemmRowCtx rc = row < M ? gemm_epilogue_row(ep, row) : GemmRowCtx{0.f, 1.f};
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -126,7 +127,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    gemm_epilogue_chunk(ep, row, col, v);
+                    gemm_epilogue_chunk(ep, row, col, v, rc);
                 }
             }
         }
@@ -300,6 +301,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
             const int m0 = ((st / stn) * CM + mi) * BM, n0 = ((st % stn) * CN + ni) * BN;
             const uint32_t as = lt & 1u;
             const int row = m0 + quad * 32 + lane;
+            const GemmRowCtx rc = (row < M && m0 < M) ? gemm_epilogue_row(ep, row) : GemmRowCtx{0.f, 1.f};   // under the MMA wait
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
@@ -314,7 +316,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                        gemm_epilogue_chunk(ep, row, col, v);
+                        gemm_epilogue_chunk(ep, row, col, v, rc);
                     }
                 }
             }
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(128) gemm_bf16_simt_kernel(const bf16* __restr
         __syncthreads();
     }
     const int row = m0 + tid;
-    if (row < M && n0 < N) gemm_epilogue_chunk(ep, row, n0, acc);
+    if (row < M && n0 < N) gemm_epilogue_chunk(ep, row, n0, acc, gemm_epilogue_row(ep, row));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,7 +35,22 @@ struct GemmEpilogue {
     // B is a constant (a weight matrix no kernel of the stream writes): its first tiles may be fetched before the
     // programmatic-dependent-launch wait, i.e. while the previous kernel is still draining
     int b_const = 0;
+    // ---- LayerNorm folded into the neighbouring GEMMs (no LayerNorm launch on the forward chain) ----
+    // producer side (the GEMM that writes a residual-stream row, N = D): per 32-column chunk of the FINAL value the pair
+    // (sum, centred sum of squares) goes to stat_part[orow * stat_nparts + col / 32]
+    float2* stat_part = nullptr;
+    int stat_nparts = 0;
+    // consumer side (A = the bf16 copy of the RAW residual stream, B = W * gamma): the row's (mean, rstd) are merged
+    // from the producer's partials and applied to the accumulator, v = rstd * (acc - mean * colsum[col]) (+ bias = the
+    // folded bias b + W beta); the column-0 chunk writes (mean, rstd) to ln_stat_out[row] for the LayerNorm backward
+    const float2* ln_part = nullptr;
+    int ln_nparts = 0;
+    const float* ln_colsum = nullptr;   // [N]: sum over k of bf16(W[n,k] * gamma[k])
+    float2* ln_stat_out = nullptr;
+    float ln_eps = 0.f;
 };
+
+struct GemmRowCtx { float mean, rstd; };
 
 enum GemmImpl : int { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1, GEMM_IMPL_TCGEN05_TILE = 2 };
 
@@ -48,8 +63,41 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, i
 int make_tmap_bf16(CUtensorMap* tm, const bf16* ptr, int rows, int cols, int ld, int box_rows);
 
 #ifdef __CUDACC__
+// Per-row context of the epilogue (computed once per tile and thread, before the accumulator is waited for): the
+// LayerNorm statistics of `row` merged from the producer's per-chunk partials (Chan's formula; 32 values per part).
+__device__ __forceinline__ GemmRowCtx gemm_epilogue_row(const GemmEpilogue& ep, int row) {
+    GemmRowCtx rc{0.f, 1.f};
+    if (ep.ln_part) {
+        const float2* p = ep.ln_part + (size_t)row * ep.ln_nparts;
+        float sum = 0.f;
+        for (int i = 0; i < ep.ln_nparts; ++i) sum += p[i].x;
+        const float inv_n = 1.f / (32.f * ep.ln_nparts);
+        const float mean = sum * inv_n;
+        float m2 = 0.f;
+        for (int i = 0; i < ep.ln_nparts; ++i) {
+            const float2 q = p[i];
+            const float d = q.x * (1.f / 32.f) - mean;
+            m2 += q.y + 32.f * d * d;
+        }
+        rc.mean = mean;
+        rc.rstd = rsqrtf(m2 * inv_n + ep.ln_eps);
+    }
+    return rc;
+}
+
 // Shared epilogue: 32 consecutive accumulator columns [col, col+32) of GEMM row `row`.
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int row, int col, float (&v)[32]) {
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int row, int col, float (&v)[32],
+                                                    const GemmRowCtx rc = GemmRowCtx{0.f, 1.f}) {
+    if (ep.ln_part) {
+        const float4* c4 = reinterpret_cast<const float4*>(ep.ln_colsum + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 c = __ldg(c4 + j);
+            v[4 * j + 0] = rc.rstd * (v[4 * j + 0] - rc.mean * c.x); v[4 * j + 1] = rc.rstd * (v[4 * j + 1] - rc.mean * c.y);
+            v[4 * j + 2] = rc.rstd * (v[4 * j + 2] - rc.mean * c.z); v[4 * j + 3] = rc.rstd * (v[4 * j + 3] - rc.mean * c.w);
+        }
+        if (ep.ln_stat_out && col == 0) ep.ln_stat_out[row] = make_float2(rc.mean, rc.rstd);
+    }
     if (ep.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);
 #pragma unroll
@@ -106,6 +154,16 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpilogue& ep, int 
             const float4 r = r4[j];
             v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
         }
+    }
+    if (ep.stat_part) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += v[j];
+        const float mc = sum * (1.f / 32.f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m2 += (v[j] - mc) * (v[j] - mc);
+        ep.stat_part[(size_t)orow * ep.stat_nparts + (col >> 5)] = make_float2(sum, m2);
     }
     if (ep.c32) {
         float4* c4 = reinterpret_cast<float4*>(ep.c32 + (size_t)orow * ep.ldc32 + col);

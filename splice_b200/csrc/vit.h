@@ -69,6 +69,9 @@ private:
     struct LayerW {
         const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
         const bf16 *qkv_w, *qkv_wT, *proj_w, *proj_wT, *fc1_w, *fc1_wT, *fc2_w, *fc2_wT;
+        // LayerNorm folded into the consuming GEMM: W * gamma (and its transpose), column sums of the bf16 matrix, b + W beta
+        const bf16 *qkv_wf, *qkv_wfT, *fc1_wf, *fc1_wfT;
+        const float *qkv_cs, *qkv_bf, *fc1_cs, *fc1_bf;
     };
     struct Slot {
         int S = 0, t = 0, gh = 0, gw = 0, n_grad = 0, oh = 0, ow = 0, n_full = 0;
@@ -82,6 +85,8 @@ private:
         std::vector<bf16*> qkv, o, hpre;     // per layer
         std::vector<float*> lse, st1, st2;   // per layer
         bf16 *a16 = nullptr, *h16 = nullptr;
+        bf16 *xa16 = nullptr, *xb16 = nullptr;        // bf16 copies of the raw residual stream (x0 / x1 of the current layer)
+        float2 *sp_a = nullptr, *sp_b = nullptr;      // their per-32-column (sum, M2) partials [M][D/32]
         // backward
         float *g = nullptr, *da = nullptr, *delta = nullptr, *dpatch = nullptr;
         bf16 *g16 = nullptr, *dh16 = nullptr, *do16 = nullptr, *dqkv16 = nullptr;
@@ -91,6 +96,9 @@ private:
     VitDesc d_;
     float* w32_ = nullptr;
     bf16* w16_ = nullptr;
+    bf16* wf16_ = nullptr;      // folded matrices
+    float* wf32_ = nullptr;     // their column sums and folded biases
+    bool ln_fused_ = false;     // SPLICE_B200_LN_FUSED=1: LayerNorm folded into the qkv / fc1 GEMMs (measured slower: vit.cu create())
     const float *cls_ = nullptr, *pos_ = nullptr, *pe_b_ = nullptr, *norm_g_ = nullptr, *norm_b_ = nullptr;
     const bf16 *pe_w_ = nullptr, *pe_wT_ = nullptr;
     std::vector<LayerW> L_;
