@@ -8,6 +8,13 @@ The input stream is unchanged: the worker calls `dataset[0]` in order from a sin
 RNGs are consumed exactly as in the reference loop (nothing else draws from them once the models are built), and the
 `step` tensor - which the dataset mutates in place (Dataset.py:57,63) - is snapshotted per sample. Tensors are pinned
 when CUDA is available so that the host -> device copy of InputStager is asynchronous.
+
+`mode="process"` runs the same worker in a forked child instead of a thread: PIL's augmentation holds the GIL for most of
+its 6 ms (224 px) and the optimisation loop itself is ~2 ms of Python per step, so a worker THREAD serialises with the
+loop (measured 127 it/s against 180 for the bare step); a forked child inherits the generator states at the moment the
+feed is created - exactly the states the inline loop would draw from - and never touches CUDA (PIL / CPU tensors only;
+samples come back through torch.multiprocessing's shared memory and are pinned by the parent). Device-side datasets
+(data/device_aug.py) need the thread mode.
 """
 from __future__ import annotations
 
@@ -17,11 +24,63 @@ import threading
 import torch
 
 
+def _child_main(dataset, n, q, stop):
+    """Body of the forked worker: no CUDA, single-threaded torch ops (an OpenMP team inherited through fork may hang)."""
+    import gc
+    import os
+
+    # The child inherits every Python object of the parent, CUDA tensors of earlier runs included. Freeing one of them here
+    # (cyclic GC) calls into a CUDA runtime that is not usable after fork ("initialization error" -> std::terminate):
+    # freeze what was inherited, collect nothing, and leave through os._exit so that no finaliser runs either.
+    gc.disable()
+    gc.freeze()
+    try:
+        torch.set_num_threads(1)
+        for _ in range(n):
+            if stop.is_set():
+                return
+            sample = dataset[0]
+            out = {k: ((v.clone() if k == 'step' else v.contiguous()) if torch.is_tensor(v) else v) for k, v in sample.items()}
+            while not stop.is_set():
+                try:
+                    q.put(out, timeout=0.1)
+                    break
+                except queue.Full:
+                    continue
+        # the tensors travel as file descriptors served by THIS process: stay until the consumer has taken the last one
+        stop.wait(timeout=3600)
+    except BaseException as e:  # noqa: BLE001 - surfaced to the consumer
+        try:
+            q.put(RuntimeError(f"prefetch worker failed: {e!r}"))
+            stop.wait(timeout=60)
+        except BaseException:  # noqa: BLE001
+            pass
+    finally:
+        try:
+            q.close()
+            q.join_thread()
+        except BaseException:  # noqa: BLE001
+            pass
+        os._exit(0)
+
+
 class PrefetchedSamples:
-    def __init__(self, dataset, n_samples: int, depth: int = 4, pin: bool | None = None):
+    def __init__(self, dataset, n_samples: int, depth: int = 4, pin: bool | None = None, mode: str = "thread"):
         self.dataset = dataset
         self.n = n_samples
         self.pin = torch.cuda.is_available() if pin is None else pin
+        self.mode = mode
+        if mode == "process":
+            import torch.multiprocessing as mp
+
+            ctx = mp.get_context("fork")
+            self._q = ctx.Queue(maxsize=max(1, depth))
+            self._stop = ctx.Event()
+            self._worker = ctx.Process(target=_child_main, args=(dataset, n_samples, self._q, self._stop), daemon=True)
+            self._worker.start()
+            return
+        if mode != "thread":
+            raise ValueError(f"prefetch mode {mode!r}: 'thread' or 'process'")
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
         self._stop = threading.Event()
         # torch.default_generator, numpy's global RandomState and python's `random` are process-wide: the worker continues
@@ -62,6 +121,8 @@ class PrefetchedSamples:
         item = self._q.get()
         if isinstance(item, BaseException):
             raise item
+        if self.mode == "process" and self.pin:     # the child cannot pin (no CUDA there): one host copy per tensor here
+            item = {k: (v.pin_memory() if torch.is_tensor(v) and k != 'step' else v) for k, v in item.items()}
         return item
 
     def __iter__(self):
@@ -76,6 +137,8 @@ class PrefetchedSamples:
         except queue.Empty:
             pass
         self._worker.join(timeout=5)
+        if self.mode == "process" and self._worker.is_alive():
+            self._worker.terminate()
 
     # pass-through used by the image-logging branch of the loop (train.py:72-73)
     def get_A(self):

@@ -72,7 +72,13 @@ def train_model(dataroot, callback=None, overrides=None, vit_state_dict=None):
     imglog = AsyncImageLog(cfg['dataroot'], callback) if log is not None else None
     A_full = None
     depth = int(cfg.get('prefetch', 4))
-    feed = PrefetchedSamples(dataset, cfg['n_epochs'], depth=depth) if depth > 0 else None
+    # cfg['prefetch_mode']: 'thread' (default; required by the device-side dataset, whose worker issues CUDA work) or
+    # 'process' (PIL dataset only: a forked child that shares no GIL with this loop; measured equal within box noise at
+    # 224 px, so the simpler thread stays the default)
+    mode = cfg.get('prefetch_mode', 'thread')
+    if isinstance(dataset, DeviceAugmentedDataset):
+        mode = 'thread'
+    feed = PrefetchedSamples(dataset, cfg['n_epochs'], depth=depth, mode=mode) if depth > 0 else None
     with tqdm(range(1, cfg['n_epochs'] + 1)) as tepoch:
         for epoch in tepoch:
             inputs = stage(feed.next() if feed is not None else dataset[0])

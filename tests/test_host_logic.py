@@ -196,17 +196,22 @@ def test_prefetched_samples_reproduce_the_inline_stream(tmp_path):
     for _ in range(n):
         s = ds[0]
         inline.append({k: v.clone() for k, v in s.items()})
-    seed()
-    feed = PrefetchedSamples(SingleImageDataset(cfg), n, depth=3, pin=False)
-    got = list(feed)
-    feed.close()
-    assert len(got) == n
+    for mode in ("thread", "process"):      # the forked worker inherits the generator states the inline loop would draw from
+        seed()
+        feed = PrefetchedSamples(SingleImageDataset(cfg), n, depth=3, pin=False, mode=mode)
+        got = list(feed)
+        feed.close()
+        assert len(got) == n
+        _same_stream(inline, got)
+
+
+def _same_stream(inline, got):
     for a, b in zip(inline, got):
         assert a.keys() == b.keys()
         for k in a:
             assert torch.equal(a[k], b[k]), k
     assert "A" in got[0] and "A" in got[75] and "A" not in got[1]
-    assert [float(g["step"]) for g in got] == [float(i) for i in range(n)]
+    assert [float(g["step"]) for g in got] == [float(i) for i in range(len(got))]
 
 
 def test_device_aug_feed_consumes_the_reference_random_stream(tmp_path):

@@ -42,7 +42,8 @@ if fullres:
     variants = (("PIL feed, prefetch=4", {}), ("device-side feed (device_aug), prefetch=4", {"device_aug": True}),
                 ("device-side feed, image logging off", {"device_aug": True, "log_images_freq": 10 ** 9}))
 else:
-    variants = (("prefetch=4, async log (default)", {}), ("prefetch=0 (inline sampling)", {"prefetch": 0}),
+    variants = (("prefetch=4, async log (default)", {}), ("prefetch=4 in a forked worker", {"prefetch_mode": "process"}),
+                ("prefetch=0 (inline sampling)", {"prefetch": 0}),
                 ("prefetch=0, log_sync (reference loop semantics)", {"prefetch": 0, "log_sync": True}),
                 ("prefetch=4, image logging off", {"log_images_freq": 10 ** 9}),
                 ("device-side feed (device_aug), prefetch=4", {"device_aug": True}))
