@@ -17,24 +17,13 @@
 // Round-1 kernels are direct fp32 SIMT convolutions (bit-comparable to the reference's fp32 CPU path).
 #include "generator.h"
 
+#include "conv_tc.h"
+#include "gen_dev.cuh"
+
 namespace splice {
 
 static constexpr int TH = 8, TW = 32;    // output tile of the conv kernels (256 threads, one pixel each)
-static constexpr float LRELU = 0.2f;
 
-struct InTf {               // per-channel transform applied to a raw tensor when it is consumed
-    const float4* k;        // (mean, invstd, a, b): value -> a*value + b ; nullptr = identity
-    int lrelu;
-};
-
-__device__ __forceinline__ float apply_tf(const InTf& tf, int c, float v) {
-    if (tf.k) {
-        const float4 k = tf.k[c];
-        v = fmaf(k.z, v, k.w);
-        if (tf.lrelu && v < 0.f) v *= LRELU;
-    }
-    return v;
-}
 // block-wide sums of NV values over 256 threads; result broadcast to every thread. red: >= 8*NV floats.
 template <int NV>
 __device__ __forceinline__ void block_reduce_vec(float (&v)[NV], float* red) {
@@ -56,95 +45,6 @@ __device__ __forceinline__ void block_reduce_vec(float (&v)[NV], float* red) {
     }
 }
 
-
-// -------------------------------------------------------------------------------------------------
-// BatchNorm statistics without a second launch: every block that produced a (count, mean, M2) partial of a channel
-// group takes a ticket; the block that draws the last ticket merges the partials of that group (fixed order: the
-// result does not depend on which block happens to be last) and writes the per-channel constants. The ticket counters
-// live in the slot, start at zero and are reset by the finishing block, so captured graphs can be replayed.
-// -------------------------------------------------------------------------------------------------
-struct BnFin {
-    const float* gamma;
-    const float* beta;
-    float4* konst;       // (mean, invstd, a, b) per channel; nullptr = no statistics wanted
-    float2* bstat;       // (mean, unbiased variance) for the running-statistics update
-    int* counter;        // one ticket counter per channel group of this layer
-    float eps;
-};
-
-// Merge of the (count, mean, M2) partials [nparts][C][3] of channel c by one warp, in double precision and in a fixed
-// order: total count and mean first, then M2 = sum(M2_i + n_i (mean_i - mean)^2) (the pairwise update of Chan et al.
-// summed over all parts; no divisions inside the loops, partials fetched eight at a time so that the L2 loads overlap).
-// Lane 0 writes the constants.
-__device__ __forceinline__ void bn_merge_channel(const float* part, int nparts, int C, int c, const BnFin& f) {
-    const int lane = threadIdx.x & 31;
-    double n = 0.0, s1 = 0.0;
-    for (int i0 = lane; i0 < nparts; i0 += 32 * 8) {
-        float nb[8], mb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            nb[u] = 0.f; mb[u] = 0.f;
-            if (i < nparts) {
-                const float* p = part + ((size_t)i * C + c) * 3;
-                nb[u] = __ldcg(p); mb[u] = __ldcg(p + 1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { n += (double)nb[u]; s1 += (double)nb[u] * (double)mb[u]; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        n += __shfl_xor_sync(0xffffffffu, n, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    }
-    const double mean = s1 / n;
-    double M2 = 0.0;
-    for (int i0 = lane; i0 < nparts; i0 += 32 * 8) {
-        float nb[8], mb[8], Mb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            nb[u] = 0.f; mb[u] = 0.f; Mb[u] = 0.f;
-            if (i < nparts) {
-                const float* p = part + ((size_t)i * C + c) * 3;
-                nb[u] = __ldcg(p); mb[u] = __ldcg(p + 1); Mb[u] = __ldcg(p + 2);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const double d = (double)mb[u] - mean;
-            M2 += (double)Mb[u] + (double)nb[u] * d * d;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
-    if (lane == 0) {
-        const double var = M2 / n;
-        const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
-        const float a = f.gamma[c] * invstd;
-        f.konst[c] = make_float4((float)mean, invstd, a, f.beta[c] - (float)mean * a);
-        if (f.bstat) f.bstat[c] = make_float2((float)mean, (float)(n > 1.0 ? M2 / (n - 1.0) : var));
-    }
-}
-
-// Called by ALL threads of a block after thread 0 has written the block's partials of channels [c0, c0 + nch).
-// `expected` = number of blocks contributing to this channel group. Uses one int of shared memory (s_flag).
-__device__ __forceinline__ void bn_finish_if_last(const float* part, int nparts, int C, int c0, int nch, int group, int expected,
-                                                  const BnFin& f, int* s_flag) {
-    if (threadIdx.x == 0) {
-        __threadfence();                                  // partials visible before the ticket
-        const int ticket = atomicAdd(f.counter + group, 1);
-        const int last = ticket == expected - 1;
-        if (last) f.counter[group] = 0;                   // self-reset for the next launch / graph replay
-        *s_flag = last;
-    }
-    __syncthreads();
-    if (*s_flag) {
-        __threadfence();
-        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int j = w; j < nch; j += nw)
-            if (c0 + j < C) bn_merge_channel(part, nparts, C, c0 + j, f);
-    }
-}
 
 // -------------------------------------------------------------------------------------------------
 // forward convolution (+ producer BN/LeakyReLU on load, + bias, + optional sigmoid, + output statistics)
@@ -1009,6 +909,15 @@ static inline bool use_tiled(int K, int S, int H, int W) {
 }
 // ... and only when 16-row tiles fill the GPU twice over: with fewer CTAs the per-chunk staging latency of a CTA is exposed
 // (measured: 103 us against 13.5 us of the direct kernel for the 224 px layers)
+// SPLICE_B200_GEN_TC=1: the 3x3 layers that fill the GPU run on the tcgen05 (3 x TF32) implicit-GEMM kernel (conv_tc.cu)
+static inline bool use_tc(int K, int S, int N, int H, int W) {
+    static int on = -1;
+    if (on < 0) {
+        const char* v = getenv("SPLICE_B200_GEN_TC");
+        on = (v && v[0] == '1') ? 1 : 0;
+    }
+    return on && K == 3 && S == 1 && (long long)ceil_div(W, 32) * ceil_div(H, 4) * N >= 2 * 148;
+}
 static inline bool tiled_fills(int N, int Cout, int H, int W) { return (long long)ceil_div(W, 32) * ceil_div(H, 16) * ceil_div(Cout, 16) * N >= 2 * 148; }
 template <bool DGRAD>
 static int launch_conv_tiled(int K, const float* x, int N, int Cin, int H, int W, InTf tf, const float* Wt, int w_cout, int w_cin,
@@ -1056,6 +965,9 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
                            const float* bias, int Cout, float* y, int Ho, int Wo, int sigmoid, const BnOut* bn, float* stats_part,
                            float* split_part, cudaStream_t st) {
     const int P = N * Ho * Wo;
+    if (bn && !sigmoid && Hin == Ho && Win == Wo && use_tc(K, S, N, Ho, Wo))
+        return launch_conv_tc<false>(x, N, Cin, Ho, Wo, tf, Wt, Cout, Cin, bias, Cout, y, 0, stats_part,
+                                     BnFin{bn->gamma, bn->beta, bn->konst, bn->bstat, bn->counter, 1e-5f}, st);
     if (bn && !sigmoid && Hin == Ho && Win == Wo && use_tiled(K, S, Ho, Wo) && tiled_fills(N, Cout, Ho, Wo))
         return launch_conv_tiled<false>(K, x, N, Cin, Ho, Wo, tf, Wt, Cout, Cin, bias, Cout, y, 0, stats_part,
                                         BnFin{bn->gamma, bn->beta, bn->konst, bn->bstat, bn->counter, 1e-5f}, st);
@@ -1090,6 +1002,9 @@ static int launch_conv_fwd(int K, int S, const float* x, int N, int Cin, int Hin
 static int launch_conv_dgrad(int K, int S, const float* dy, int N, int Cout, int Ho, int Wo, const float* Wt, int Cin, float* dX,
                              int Hin, int Win, int accumulate, float* split_part, cudaStream_t st) {
     const int P = N * Hin * Win;
+    if (Hin == Ho && Win == Wo && use_tc(K, S, N, Hin, Win))
+        return launch_conv_tc<true>(dy, N, Cout, Hin, Win, InTf{nullptr, 0}, Wt, Cout, Cin, nullptr, Cin, dX, accumulate, nullptr,
+                                    BnFin{nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f}, st);
     if (Hin == Ho && Win == Wo && use_tiled(K, S, Hin, Win) && tiled_fills(N, Cin, Hin, Win))
         return launch_conv_tiled<true>(K, dy, N, Cout, Hin, Win, InTf{nullptr, 0}, Wt, Cout, Cin, nullptr, Cin, dX, accumulate, nullptr,
                                        BnFin{nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f}, st);
@@ -1122,6 +1037,11 @@ int gen_debug_conv(const float* x, int N, int Cin, int H, int W, const float* Wt
     SPLICE_REQUIRE(K == 1 || K == 3, "gen_debug_conv: K must be 1 or 3");
     const InTf none{nullptr, 0};
     const BnFin nofin{nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f};
+    if (tiled == 2) {   // tcgen05 implicit GEMM (3x3 only)
+        SPLICE_REQUIRE(K == 3, "gen_debug_conv: the tcgen05 kernel is 3x3 only");
+        if (!dgrad) return launch_conv_tc<false>(x, N, Cin, H, W, none, Wt, Cout, Cin, bias, Cout, y, 0, nullptr, nofin, st);
+        return launch_conv_tc<true>(x, N, Cout, H, W, none, Wt, Cout, Cin, nullptr, Cin, y, 0, nullptr, nofin, st);
+    }
     if (!dgrad) {   // y[N,Cout,H,W] = conv(x[N,Cin,H,W], Wt[Cout,Cin,K,K]) + bias
         if (tiled) return launch_conv_tiled<false>(K, x, N, Cin, H, W, none, Wt, Cout, Cin, bias, Cout, y, 0, nullptr, nofin, st);
         dim3 grid(ceil_div(N * H * W, CONV_THREADS), ceil_div(Cout, 16), 1);

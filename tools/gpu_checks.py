@@ -1411,7 +1411,7 @@ def generator_conv_kernels():
         x64 = x.double().requires_grad_(True)
         y64 = F.conv2d(x64, w.double(), b.double(), padding=K // 2)
         y64.backward(dy.double())
-        for tiled in (1, 0):
+        for tiled in ((2, 1, 0) if K == 3 else (1, 0)):      # 2 = tcgen05 3 x TF32 implicit GEMM, 1 = SIMT tiled, 0 = direct
             y = torch.empty(N, Cout, H, W, device="cuda")
             dx = torch.empty(N, Cin, H, W, device="cuda")
             _lib.check(_lib.splice_gen_debug_conv(x.data_ptr(), N, Cin, H, W, w.data_ptr(), Cout, K, b.data_ptr(), y.data_ptr(), 0, tiled,
