@@ -121,8 +121,10 @@ int VitEngine::create(VitEngine** out, const VitDesc& d, const float* packed_dev
         const char* v = getenv("SPLICE_B200_LN_FUSED");
         e->ln_fused_ = (v && v[0] == '1');
     }
-    SPLICE_CHECK_CUDA(cudaMalloc(&e->wf16_, (size_t)d.depth * 2 * (3 * D * D + 4 * D * D) * sizeof(bf16)));
-    SPLICE_CHECK_CUDA(cudaMalloc(&e->wf32_, (size_t)d.depth * 14 * D * sizeof(float)));
+    if (e->ln_fused_) {   // the folded copies (~200 MB for ViT-B) exist only when the option is on
+        SPLICE_CHECK_CUDA(cudaMalloc(&e->wf16_, (size_t)d.depth * 2 * (3 * D * D + 4 * D * D) * sizeof(bf16)));
+        SPLICE_CHECK_CUDA(cudaMalloc(&e->wf32_, (size_t)d.depth * 14 * D * sizeof(float)));
+    }
     bf16* qf = e->wf16_;
     float* pf = e->wf32_;
     const float* p = e->w32_;
@@ -132,6 +134,8 @@ int VitEngine::create(VitEngine** out, const VitDesc& d, const float* packed_dev
     // the LayerNorm (gamma, beta) in front of a Linear(cols -> rows) whose fp32 weight / bias are w / b: folded copies
     auto fold = [&](const float* w, const float* b, const float* g, const float* bt, int rows, int cols, const bf16** wf,
                     const bf16** wfT, const float** cs, const float** bf) {
+        *wf = nullptr; *wfT = nullptr; *cs = nullptr; *bf = nullptr;
+        if (!e->ln_fused_) return;
         bf16* a = qf; qf += (size_t)rows * cols;
         bf16* t2 = qf; qf += (size_t)rows * cols;
         float* c1 = pf; pf += rows;
