@@ -1,7 +1,7 @@
 // splice_b200 — 3x3 stride-1 "same" convolution of the generator as an implicit GEMM on tcgen05 (kind::tf32), forward and
 // data gradient. Replaces nn.Conv2d (models/unet/common.py:99-124) for the high-resolution layers that fill the GPU.
 //
-//   D[128 pixels, N = Cout] = A[128 pixels, K = Cin * 9] * B[N, K]^T,   k = ci * 9 + (ky * 3 + kx)
+//   D[128 pixels, N = Cout] = A[128 pixels, K = 9 * Cp] * B[N, K]^T,   k = (ky * 3 + kx) * Cp + ci,  Cp = Cin rounded up to 4
 //
 // fp32 accuracy on tensor cores: every operand is split into two TF32 numbers, a = hi + lo with hi = a truncated to
 // TF32 (the 19 bits the tensor core reads) and lo = a - hi (exact in fp32), and three products are accumulated in fp32
@@ -16,6 +16,10 @@
 // for the data gradient). One thread issues 4 k-steps x 3 MMAs and commits to an mbarrier; two such CTAs per SM overlap one
 // CTA's operand build with the other's MMAs. Instruction count per (pixel, ci, tap): ~10, independent of Cout - the
 // SIMT tiled kernel needs ~1.1 per output channel.
+// Measured (B200, netG at 896 px, SPLICE_B200_GEN_TC=1): 3-7e-6 of fp64 conv2d, every generator check green; forward
+// 1.6x SLOWER than the SIMT tiled kernel (long reductions: every element a global gather + producer transform), data
+// gradient 5 % faster (short reductions, wide N). Off by default; profiles/ANALYSIS_r2.md lists what it needs next
+// (input tile staged in shared memory, double-buffered operand tiles, TMA im2col from NHWC copies).
 //
 // Epilogue (forward): tcgen05.ld of the accumulator row, bias, store (a warp = 32 consecutive pixels of a row: coalesced
 // per channel), per-tile (count, mean, M2) BatchNorm partials and the last-ticket merge, exactly like the other kernels.
@@ -75,7 +79,7 @@ conv_tc_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, cons
     const bool pix_ok = oy < H && ox < W;
     const size_t plane = (size_t)H * W;
     const float* xn = x + (size_t)n * Cin * plane;
-    const int Ktot = Cin * 9, num_kb = (Ktot + TCK - 1) / TCK;
+    const int Ktot = ((Cin + 3) & ~3) * 9, num_kb = (Ktot + TCK - 1) / TCK;
 
     if (tid == 0) {
         mbar_init(mma_bar, 1);
@@ -103,7 +107,14 @@ conv_tc_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, cons
         coff[k] = min(max(ix, 0), W - 1);
     }
 
-    int ci = 0, tap = 0;      // (reduction channel, tap) of the next element of this thread's row: advances with k
+    // Reduction order: k = tap * Cp + ci with Cp = Cin rounded up to 4 (tap-major): the 4 elements of a 16-byte chunk share one
+    // tap - one offset, one validity bit - and are 4 consecutive channels; (tap, ci) advance without divisions.
+    // (The first version used k = ci * 9 + tap: every element decoded its own tap - ~30 instructions per element.)
+    const int Cp = (Cin + 3) & ~3;
+    unsigned okmask = 0;      // bit tap: the tap's source pixel lies inside the image
+#pragma unroll
+    for (int t = 0; t < 9; ++t) okmask |= (rok[t / 3] && cok[t % 3]) ? (1u << t) : 0u;
+    int ci = 0, tap = 0;      // (first channel, tap) of this thread's next chunk
     for (int kb = 0; kb < num_kb; ++kb) {
         if (kb > 0) {         // the MMAs of the previous k-block have read the operand tiles
             mbar_wait(mma_bar, (uint32_t)((kb - 1) & 1));
@@ -112,41 +123,45 @@ conv_tc_kernel(const float* __restrict__ x, int Cin, int H, int W, InTf tf, cons
         // ---- A: this pixel's 32 im2col values of the k-block, split, swizzled rows
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (tap < 9 && ((okmask >> tap) & 1u)) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const int off = (ky == 0 ? roff[0] : ky == 1 ? roff[1] : roff[2]) + (kx == 0 ? coff[0] : kx == 1 ? coff[1] : coff[2]);
+                const float* src = xn + (size_t)ci * plane + off;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ci + j < Cin) {
+                        float t = src[(size_t)j * plane];
+                        if (!DGRAD && tf.k) {
+                            const float4 k4 = __ldg(tf.k + ci + j);
+                            t = fmaf(k4.z, t, k4.w);
+                            if (tf.lrelu) t = t < 0.f ? t * LRELU : t;
+                        }
+                        v[j] = t;
+                    }
+            }
             float hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float v = 0.f;
-                if (ci < Cin) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const bool ok = (ky == 0 ? rok[0] : ky == 1 ? rok[1] : rok[2]) && (kx == 0 ? cok[0] : kx == 1 ? cok[1] : cok[2]);
-                    if (ok) {
-                        const int ro = ky == 0 ? roff[0] : ky == 1 ? roff[1] : roff[2];
-                        const int co = kx == 0 ? coff[0] : kx == 1 ? coff[1] : coff[2];
-                        v = xn[(size_t)ci * plane + ro + co];
-                        if (!DGRAD && tf.k) {
-                            const float4 k4 = __ldg(tf.k + ci);
-                            v = fmaf(k4.z, v, k4.w);
-                            if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
-                        }
-                    }
-                }
-                hi[j] = tf32_hi(v);
-                lo[j] = v - hi[j];
-                if (++tap == 9) { tap = 0; ++ci; }
+                hi[j] = tf32_hi(v[j]);
+                lo[j] = v[j] - hi[j];
             }
             st_row_chunk(a_hi, tid, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
             st_row_chunk(a_lo, tid, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
+            ci += 4;
+            if (ci >= Cp) { ci = 0; ++tap; }
         }
-        // ---- B: the weight k-block [NT rows = output channels][32], split the same way
+        // ---- B: the weight k-block [NT rows = output channels][32] in the same k order, split the same way
         for (int idx = tid; idx < NT * 8; idx += 128) {
             const int o = idx >> 3, c = idx & 7;
+            const int k0 = kb * TCK + c * 4;
+            const int tp = k0 / Cp, cr0 = k0 - tp * Cp;          // one tap, 4 consecutive reduction channels
             float hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = kb * TCK + c * 4 + j;
+                const int cr = cr0 + j;
                 float wv = 0.f;
-                if (k < Ktot && o < Cout) {
-                    const int cr = k / 9, tp = k - cr * 9;
+                if (tp < 9 && cr < Cin && o < Cout) {
                     if (DGRAD) wv = __ldg(Wt + ((size_t)cr * w_cin + o) * 9 + (8 - tp));      // transposed, flipped
                     else wv = __ldg(Wt + ((size_t)o * w_cin + cr) * 9 + tp);
                 }
