@@ -216,6 +216,39 @@ SPLICE_API int splice_gen_debug_conv(const void* x, int N, int Cin, int H, int W
  * concurrently executed netG backward passes into .grad (ref: autograd gradient accumulation, train.py:56,78) */
 SPLICE_API int splice_accumulate(void* dst, const void* const* srcs, int n_src, size_t n, void* stream);
 
+/* ---- generator, other skip() configurations ------------------------------------------------------------ */
+/* skip() with arguments other than the defaults (ref: models/unet/skip.py:4-102; the one the reference builds is inversion.py:21-25:
+ * 6 scales, 32 input channels, 7x7 / 5x5 / 3x3 filters, pad = 'reflection' -> nn.ReflectionPad2d, models/unet/common.py:113-118).
+ * The configuration is data; strided down-sampling, bilinear x2 up-sampling, LeakyReLU(0.2), BatchNorm2d in training mode,
+ * need1x1_up and need_bias are fixed. Filter sizes 1, 3, 5 or 7; at most 160 channels per tensor. */
+#define SPLICE_GENX_MAX_SCALES 8
+typedef struct SpliceGenXConfig {
+    int n_scales;                              /* len(num_channels_down) */
+    int in_channels, out_channels;             /* num_input_channels, num_output_channels */
+    int ch_down[SPLICE_GENX_MAX_SCALES];       /* num_channels_down */
+    int ch_up[SPLICE_GENX_MAX_SCALES];         /* num_channels_up */
+    int ch_skip[SPLICE_GENX_MAX_SCALES];       /* num_channels_skip (all > 0) */
+    int k_down[SPLICE_GENX_MAX_SCALES];        /* filter_size_down */
+    int k_up[SPLICE_GENX_MAX_SCALES];          /* filter_size_up */
+    int k_skip;                                /* filter_skip_size */
+    int reflect;                               /* pad: 0 = 'zero', 1 = 'reflection' */
+    int sigmoid;                               /* need_sigmoid */
+} SpliceGenXConfig;
+SPLICE_API int splice_genx_create(const SpliceGenXConfig* cfg, void** ctx);
+SPLICE_API int splice_genx_destroy(void* ctx);
+/* number of parameter tensors (22 per scale + 2, netG.parameters() order) and of BatchNorm2d layers (6 per scale, module order) */
+SPLICE_API int splice_genx_counts(void* ctx, int* n_params, int* n_bn);
+/* Pointer tables (host arrays of device pointers, copied): fp32 parameters; fp32 gradients (NULL table = forward only); BatchNorm
+ * running_mean / running_var (fp32) and num_batches_tracked (int64) (NULL tables = never update running statistics). */
+SPLICE_API int splice_genx_bind(void* ctx, void* const* params, void* const* grads, void* const* running_mean,
+                                void* const* running_var, void* const* num_batches_tracked);
+/* out[N,out_channels,H,W] = net(x[N,in_channels,H,W]) (ref: net(net_input), inversion.py:65); keep != 0 retains the activations for
+ * splice_genx_backward (one pass at a time; a later forward replaces it) */
+SPLICE_API int splice_genx_forward(void* ctx, const void* x, int N, int H, int W, void* out, int keep, int update_running, void* stream);
+/* parameter gradients of the kept forward given dout = d loss / d out (ref: loss.backward(), inversion.py:68); accumulate != 0: += */
+SPLICE_API int splice_genx_backward(void* ctx, const void* dout, int accumulate, void* stream);
+SPLICE_API int splice_genx_set_graphs(void* ctx, int on);
+
 /* ---- optimiser -------------------------------------------------------------------------------------- */
 /* One Adam step over n_tensors fp32 tensors (host arrays of device pointers / element counts).
  * `step` is the 1-based step count AFTER the increment.  ref: get_optimizer util/util.py:28-32 -> torch.optim.Adam */

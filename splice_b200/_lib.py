@@ -112,6 +112,16 @@ class SpliceGenPointers(C.Structure):
                 ("num_batches_tracked", c_void_p * GEN_BN)]
 
 
+GENX_MAX_SCALES = 8
+
+
+class SpliceGenXConfig(C.Structure):
+    _fields_ = [("n_scales", c_int), ("in_channels", c_int), ("out_channels", c_int),
+                ("ch_down", c_int * GENX_MAX_SCALES), ("ch_up", c_int * GENX_MAX_SCALES), ("ch_skip", c_int * GENX_MAX_SCALES),
+                ("k_down", c_int * GENX_MAX_SCALES), ("k_up", c_int * GENX_MAX_SCALES),
+                ("k_skip", c_int), ("reflect", c_int), ("sigmoid", c_int)]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -165,6 +175,23 @@ splice_gen_set_graphs = _sig("splice_gen_set_graphs", c_int, [c_void_p, c_int])
 splice_gen_backward = _sig("splice_gen_backward", c_int, [c_void_p, C.POINTER(SpliceGenPointers), c_void_p, c_int, c_int, c_void_p])
 splice_gen_debug_conv = _sig("splice_gen_debug_conv", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                                                c_void_p, c_int, c_int, c_void_p])
+GENX_SIGNATURES = {   # shared with the CPU emulation build of the same entry points (tests/emu)
+    "splice_genx_create": (c_int, [C.POINTER(SpliceGenXConfig), C.POINTER(c_void_p)]),
+    "splice_genx_destroy": (c_int, [c_void_p]),
+    "splice_genx_counts": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
+    "splice_genx_bind": (c_int, [c_void_p, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
+                                 C.POINTER(c_void_p)]),
+    "splice_genx_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "splice_genx_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "splice_genx_set_graphs": (c_int, [c_void_p, c_int]),
+}
+splice_genx_create = _sig("splice_genx_create", *GENX_SIGNATURES["splice_genx_create"])
+splice_genx_destroy = _sig("splice_genx_destroy", *GENX_SIGNATURES["splice_genx_destroy"])
+splice_genx_counts = _sig("splice_genx_counts", *GENX_SIGNATURES["splice_genx_counts"])
+splice_genx_bind = _sig("splice_genx_bind", *GENX_SIGNATURES["splice_genx_bind"])
+splice_genx_forward = _sig("splice_genx_forward", *GENX_SIGNATURES["splice_genx_forward"])
+splice_genx_backward = _sig("splice_genx_backward", *GENX_SIGNATURES["splice_genx_backward"])
+splice_genx_set_graphs = _sig("splice_genx_set_graphs", *GENX_SIGNATURES["splice_genx_set_graphs"])
 splice_accumulate = _sig("splice_accumulate", c_int, [c_void_p, C.POINTER(c_void_p), c_int, c_size_t, c_void_p])
 splice_adam_step = _sig("splice_adam_step", c_int,
                         [C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
@@ -180,6 +207,8 @@ EXPORTS = [
     "splice_loss_ssim", "splice_loss_mse", "splice_keys_self_sim", "splice_weighted_total", "splice_debug_spin",
     "splice_gen_create", "splice_gen_destroy", "splice_gen_forward", "splice_gen_backward", "splice_gen_set_graphs",
     "splice_accumulate", "splice_gen_update_running", "splice_gen_debug_conv",
+    "splice_genx_create", "splice_genx_destroy", "splice_genx_counts", "splice_genx_bind", "splice_genx_forward",
+    "splice_genx_backward", "splice_genx_set_graphs",
     "splice_adam_step", "splice_vit_profile_enable", "splice_vit_profile_read",
 ]
 

@@ -1,6 +1,10 @@
 // splice_b200 — device-side pieces shared by the generator's kernels (generator.cu, conv_tc.cu)
 #pragma once
+#ifdef SPLICE_EMU
+#include "cuda_emu.h"   // tests/emu: CPU emulation of the CUDA subset these kernels use (host-side checks without a GPU)
+#else
 #include "common.cuh"
+#endif
 
 namespace splice {
 

@@ -68,6 +68,13 @@ class NativeSkip(nn.Sequential):
         self._priv_ptrs: dict = {}
         self.concurrent = True                        # independent netG calls of a step run on parallel streams
 
+    def __getstate__(self):
+        # copy.deepcopy / pickle: the copy owns its tensors but not this module's engine, pointer tables, streams or gradient buffers
+        st = self.__dict__.copy()
+        st.update(_params_cache=None, _bns_cache=None, _eng=None, _ptrs=None, _ptr_sig=None, _flat_grad=None, _grad_views=[],
+                  _slot_tokens=[None] * 4, _side_streams=[], _priv_grads=[], _priv_ptrs={})
+        return st
+
     # ---- pointer tables ----------------------------------------------------------------------------
     def _param_list(self) -> List[torch.nn.Parameter]:
         # cached: walking the module tree costs ~0.1 ms and this is asked for several times per step. The Parameter

@@ -1,9 +1,10 @@
 """Building blocks of the generator (drop-in for the reference's models/unet/common.py:11-124).
 
-Only what the default-argument `skip()` of the training loop needs is native: zero-padded strided convs,
-BatchNorm2d (always in training mode), LeakyReLU(0.2), bilinear x2 upsampling, channel concat with centre
-crop. The DIP leftovers the loop never reaches (GenNoise, Swish/ELU, lanczos/avg/max down-samplers,
-reflection padding) are out of scope and raise NotImplementedError.
+What the reference's two skip() call sites need is native (models/networks.py:57 default arguments; inversion.py:21-25
+reflection padding, 7x7 / 5x5 filters): zero- or reflection-padded strided convs, BatchNorm2d (always in training
+mode), LeakyReLU(0.2), bilinear x2 upsampling, channel concat with centre crop. The DIP leftovers neither call site
+reaches (GenNoise, Swish/ELU, lanczos/avg/max down-samplers) are out of scope and raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -61,7 +62,9 @@ def bn(num_features):
 def conv(in_f, out_f, kernel_size, stride=1, bias=True, pad='zero', downsample_mode='stride'):
     if stride != 1 and downsample_mode != 'stride':
         raise NotImplementedError(f"downsample_mode {downsample_mode!r} is outside the splice_b200 hot path")
-    if pad != 'zero':
+    if pad not in ('zero', 'reflection'):
         raise NotImplementedError(f"pad {pad!r} is outside the splice_b200 hot path")
     to_pad = int((kernel_size - 1) / 2)
+    if pad == 'reflection':   # ref common.py:113-118: the padder is child "0", the conv child "1" (state_dict keys)
+        return nn.Sequential(nn.ReflectionPad2d(to_pad), nn.Conv2d(in_f, out_f, kernel_size, stride, padding=0, bias=bias))
     return nn.Sequential(nn.Conv2d(in_f, out_f, kernel_size, stride, padding=to_pad, bias=bias))

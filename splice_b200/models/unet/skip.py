@@ -9,6 +9,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from ...generator import NativeSkip
+from ...generator_x import NativeSkipX
 from .common import Concat, act, bn, conv
 
 
@@ -65,21 +66,35 @@ def skip(
         if not last:
             fill_level(nxt, i + 1, c_down)
 
-    # the default-argument network (the only one the optimisation loop builds, models/networks.py:57) runs on the
-    # native sm_100a generator engine. Any other configuration is refused: evaluating it module by module with torch /
-    # cuDNN would be a silent second backend (north_star: no multi-backend dispatch). inversion.py's variant (6 scales,
-    # 7x7 / 5x5 filters, reflection padding) keeps using the reference's own models/unet.
+    # The default-argument network (the one the optimisation loop builds, models/networks.py:57) runs on the generator engine
+    # tuned for it (csrc/generator.cu). Other configurations made of the same building blocks - inversion.py:21-25: 6 scales,
+    # 32 input channels, 7x7 / 5x5 / 3x3 filters, reflection padding - run on the generalised engine (csrc/generator_x.cu).
+    # Anything else (other activations / down-samplers / nearest up-sampling / no bias) is refused: evaluating it module by
+    # module with torch / cuDNN would be a silent second backend (north_star: no multi-backend dispatch).
     is_default = (num_input_channels == 3 and num_output_channels == 3 and list(num_channels_down) == [16, 32, 64, 128, 128]
                   and list(num_channels_up) == [16, 32, 64, 128, 128] and list(num_channels_skip) == [4, 4, 4, 4, 4]
                   and k_down == [3] * 5 and k_up == [3] * 5 and filter_skip_size == 1 and need_sigmoid and need_bias
                   and pad == 'zero' and up_modes == ['bilinear'] * 5 and down_modes == ['stride'] * 5
                   and act_fun == 'LeakyReLU' and need1x1_up)
-    if not is_default:
-        raise NotImplementedError("splice_b200's generator engine implements the default-argument skip() network only "
-                                  "(5 scales [16,32,64,128,128], 3x3 / 1x1 filters, zero padding, bilinear up-sampling, "
-                                  "strided down-sampling, LeakyReLU, sigmoid); use the reference's models/unet for other "
-                                  "configurations")
-    model = NativeSkip()
+    if is_default:
+        model = NativeSkip()
+    else:
+        filters = set(k_down) | set(k_up) | {filter_skip_size}
+        widest = max([num_input_channels] + [num_channels_skip[i] + (num_channels_down[i] if i == n - 1 else num_channels_up[i + 1])
+                                              for i in range(n)] + list(num_channels_down) + list(num_channels_up))
+        supported = (act_fun == 'LeakyReLU' and need1x1_up and need_bias and not (need_tanh and not need_sigmoid)
+                     and up_modes == ['bilinear'] * n and down_modes == ['stride'] * n and pad in ('zero', 'reflection')
+                     and all(c > 0 for c in num_channels_skip) and filters <= {1, 3, 5, 7} and 1 <= n <= 8
+                     and widest <= 160 and 1 <= num_output_channels <= 16)
+        if not supported:
+            raise NotImplementedError("splice_b200's generator engines implement skip() networks built from strided convs with bias "
+                                      "(filter sizes 1/3/5/7, zero or reflection padding), BatchNorm, LeakyReLU, bilinear "
+                                      "up-sampling, non-empty skip branches and 1x1 up convs, with at most 8 scales and 160 "
+                                      "channels per tensor; use the reference's models/unet for other configurations")
+        model = NativeSkipX(dict(num_input_channels=num_input_channels, num_output_channels=num_output_channels,
+                                 num_channels_down=list(num_channels_down), num_channels_up=list(num_channels_up),
+                                 num_channels_skip=list(num_channels_skip), filter_size_down=k_down, filter_size_up=k_up,
+                                 filter_skip_size=filter_skip_size, pad=pad, need_sigmoid=bool(need_sigmoid)))
     fill_level(model, 0, num_input_channels)
     model.add(conv(num_channels_up[0], num_output_channels, 1, bias=need_bias, pad=pad))
     if need_sigmoid:

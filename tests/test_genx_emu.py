@@ -1,0 +1,134 @@
+"""The generalised generator engine (csrc/generator_x.cu: inversion.py's 6-scale, 7x7 / 5x5, reflection-padded skip() and
+other non-default configurations) checked WITHOUT a GPU: the same source is compiled by g++ against tests/emu/cuda_emu.h
+(kernel bodies run as CPU fibers, host orchestration unchanged) and driven through the product's own Python glue
+(splice_b200/generator_x.py), then compared with torch evaluating the module tree the reference would build
+(nn.ReflectionPad2d / Conv2d / BatchNorm2d / LeakyReLU / Upsample / Concat) and its autograd.
+
+This is test infrastructure: the product library is the nvcc build and has no CPU path; the `-m gpu` check
+`generator_inversion_variant` repeats the comparison on the real kernels.
+"""
+import copy
+import ctypes as C
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+class _EmuBackend:
+    """The emulation build behind the names generator_x.py uses on its backend."""
+
+    def __init__(self):
+        sys.path.insert(0, str(ROOT / "tests" / "emu"))
+        import build_emu
+        from splice_b200 import _lib
+
+        self.lib = C.CDLL(str(build_emu.build()))
+        for name, (restype, argtypes) in _lib.GENX_SIGNATURES.items():
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+            setattr(self, name, fn)
+        self._err = _lib.SpliceError
+
+    def check(self, rc, what=""):
+        if rc != 0:
+            raise self._err(f"{what} failed in the emulation build (rc={rc})")
+
+    @staticmethod
+    def cur_stream():
+        return None
+
+
+@pytest.fixture(scope="module")
+def emu_backend():
+    from splice_b200 import generator_x
+
+    be = _EmuBackend()
+    old = generator_x._backend
+    generator_x._backend = be
+    yield be
+    generator_x._backend = old
+
+
+def _tie_free_input(net, shape, first_seed, margin=2e-5):
+    """A seeded input on which no LeakyReLU pre-activation of the float64 evaluation is within `margin` of zero."""
+    from tools.genx_compare import tie_margin
+
+    for seed in range(first_seed, first_seed + 200):
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+        if tie_margin(net, x) > margin:
+            return x
+    raise AssertionError("no tie-free input found")
+
+
+def test_inversion_variant_matches_torch_modules(emu_backend):
+    """inversion.py:21-25's network (6 scales, 7x7 / 5x5 / 3x3, reflection padding, 32-channel noise input) at a small, odd,
+    non-square size: forward, every parameter gradient, running statistics; then a second iteration as the inversion loop runs it."""
+    from splice_b200.generator_x import NativeSkipX
+    from splice_b200.models.unet.skip import skip
+    from tools.genx_compare import compare, randomise
+
+    torch.manual_seed(0)
+    net = skip(32, 3, num_channels_down=[16, 32, 64, 128, 128, 128], num_channels_up=[16, 32, 64, 128, 128, 128],
+               num_channels_skip=[4, 4, 4, 4, 4, 4], filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3],
+               downsample_mode='stride', pad='reflection')
+    assert isinstance(net, NativeSkipX)
+    assert len(list(net.parameters())) == 134
+    randomise(net, 1)
+    x = torch.randn(1, 32, 67, 90, generator=torch.Generator().manual_seed(2))
+    compare(net, x, 3)
+    for p in net.parameters():      # optimizer.zero_grad() (inversion.py:64), then noise added to the input (inversion.py:57-62)
+        p.grad = None
+    x2 = x + 0.5 * torch.randn(x.shape, generator=torch.Generator().manual_seed(4))
+    compare(net, x2, 5)
+
+
+@pytest.mark.parametrize("pad", ["zero", "reflection"])
+def test_three_scales_strict(emu_backend, pad):
+    """Three scales of the inversion network (7x7, 7x7, 5x5; odd sizes so that strided and cropped borders are exercised) on an input
+    without LeakyReLU near-ties: every gradient as close to float64 as torch's float32 path, no allowance."""
+    from splice_b200.models.unet.skip import skip
+    from tools.genx_compare import compare, randomise
+
+    torch.manual_seed(20)
+    net = skip(32, 3, num_channels_down=[16, 32, 64], num_channels_up=[16, 32, 64], num_channels_skip=[4, 4, 4],
+               filter_size_down=[7, 7, 5], filter_size_up=[7, 7, 5], pad=pad)
+    randomise(net, 21)
+    x = _tie_free_input(net, (1, 32, 43, 58), 22)
+    compare(net, x, 23, strict=True)
+
+
+@pytest.mark.parametrize("pad", ["zero", "reflection"])
+def test_small_mixed_configuration(emu_backend, pad):
+    """A 2-scale network with batch 2, 3x3 skip filters, mixed filter sizes and no sigmoid, so that the batch dimension, the
+    accumulate path and the linear output of the generalised kernels are exercised too."""
+    from splice_b200.models.unet.skip import skip
+    from tools.genx_compare import compare, randomise
+
+    torch.manual_seed(10)
+    net = skip(5, 2, num_channels_down=[8, 12], num_channels_up=[8, 12], num_channels_skip=[3, 5], filter_size_down=[5, 3],
+               filter_size_up=[3, 7], filter_skip_size=3, need_sigmoid=False, pad=pad)
+    randomise(net, 11)
+    x = _tie_free_input(net, (2, 5, 21, 30), 12)
+    compare(net, x, 13, strict=True)
+    # gradients left in place are accumulated into (autograd semantics): the same comparison again without clearing them
+    assert all(p.grad is not None for p in net.parameters())
+    compare(net, x, 14, strict=True)
+
+
+def test_unsupported_configurations_are_refused():
+    from splice_b200.models.unet.skip import skip
+
+    with pytest.raises(NotImplementedError):
+        skip(3, 3, upsample_mode='nearest')
+    with pytest.raises(NotImplementedError):
+        skip(3, 3, act_fun='Swish')
+    with pytest.raises(NotImplementedError):
+        skip(3, 3, filter_size_down=9)
+    with pytest.raises(NotImplementedError):
+        skip(3, 3, downsample_mode='avg')

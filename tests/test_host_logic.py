@@ -63,20 +63,31 @@ def test_generator_tree_and_init_match_reference(golden_dir):
 
 
 def test_out_of_scope_generator_options_raise():
+    from splice_b200.generator import NativeSkip
+    from splice_b200.generator_x import NativeSkipX
     from splice_b200.models.unet.skip import skip
 
-    with pytest.raises(NotImplementedError):
-        skip(pad="reflection")
     with pytest.raises(NotImplementedError):
         skip(downsample_mode="lanczos2")
     with pytest.raises(NotImplementedError):
         skip(act_fun="Swish")
-    # ... and so does every other non-default configuration (no silent torch-module evaluation), e.g. inversion.py:21-25
     with pytest.raises(NotImplementedError):
-        skip(32, 3, num_channels_down=[16, 32, 64, 128, 128, 128], num_channels_up=[16, 32, 64, 128, 128, 128],
-             num_channels_skip=[4, 4, 4, 4, 4, 4], filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3])
+        skip(upsample_mode="nearest")
     with pytest.raises(NotImplementedError):
-        skip(need_sigmoid=False)
+        skip(num_channels_skip=[4, 4, 0, 4, 4])
+    # the default arguments build the engine tuned for the optimisation loop; configurations made of the same building blocks
+    # (inversion.py:21-25) the generalised native engine - never a torch-module evaluation
+    assert type(skip()) is NativeSkip
+    inv = skip(32, 3, num_channels_down=[16, 32, 64, 128, 128, 128], num_channels_up=[16, 32, 64, 128, 128, 128],
+               num_channels_skip=[4, 4, 4, 4, 4, 4], filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3],
+               downsample_mode='stride', pad='reflection')
+    assert type(inv) is NativeSkipX
+    assert type(skip(pad="reflection")) is NativeSkipX and type(skip(need_sigmoid=False)) is NativeSkipX
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        inv(torch.zeros(1, 32, 16, 16))
+    inv.eval()
+    with pytest.raises(NotImplementedError, match="training mode"):
+        inv(torch.zeros(1, 32, 16, 16))
 
 
 def test_scheduler_and_optimizer_factories():
