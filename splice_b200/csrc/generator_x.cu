@@ -578,7 +578,9 @@ int GenXEngine::configure(int N, int H, int W) {
         }
         h = hd[i]; w = wd[i];
     }
-    SPLICE_REQUIRE(hs[ns_ - 1] >= 1 && ws[ns_ - 1] >= 1, "generator: input %dx%d too small", H, W);
+    // nn.BatchNorm2d in training mode refuses a single value per channel ("Expected more than 1 value per channel when training")
+    SPLICE_REQUIRE((size_t)N * hd[ns_ - 1] * wd[ns_ - 1] > 1, "generator: input %dx%d too small: one value per channel at the deepest scale "
+                   "(BatchNorm in training mode needs more than 1)", H, W);
     const size_t io_in = (size_t)N * cfg_.in_channels * H * W, io_out = (size_t)N * cfg_.out_channels * H * W;
 
     size_t off = 0;

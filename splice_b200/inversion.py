@@ -1,0 +1,123 @@
+"""Drop-in for the reference's inversion.py (feature inversion: optimise a generator so that a DINO-ViT feature of its output
+matches the feature of a given image). Same command line, same loop (ref inversion.py:12-74):
+
+    net          = skip(32, 3, 6 scales, 7x7/5x5/3x3 filters, pad='reflection')   -> native engine csrc/generator_x.cu
+    feature(x)   = vit_extractor.get_feature_from_input(pre(x))[layer][:, 0, :]    ('cls')
+                 | vit_extractor.get_keys_from_input(pre(x), layer)               ('keys') -> native ViT engine, differentiable taps
+    loss         = MSELoss(feature(net(net_input)), feature(image)); Adam(lr = 0.01) on net.parameters()
+
+The torchvision transforms (Resize(224) + Normalize) stay torch ops, as in the reference: they are differentiable tensor ops
+between the two native engines. Extensions (keyword arguments of `invert`, not on the command line): `vit_state_dict` - DINO weights
+to use instead of torch.hub (offline runs), `callback(i, loss, net, net_input)` - called every iteration with the detached loss,
+`noise_on_device` - draw the per-iteration regularisation noise of the 'cls' mode with the CUDA generator instead of the reference's
+CPU draw + copy (a different random stream under the same seed, and ~10 ms less host work per iteration at 224 x 298).
+"""
+from __future__ import annotations
+
+from argparse import ArgumentParser
+
+import torch
+from PIL import Image
+from torchvision import transforms as T
+
+from .models.extractor import VitExtractor
+from .models.unet.skip import skip
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def invert(args, vit_state_dict=None, callback=None, noise_on_device=False):
+    if device.type != "cuda":
+        raise RuntimeError("splice_b200 runs on sm_100a only; there is no CPU fallback")
+    # load the image
+    input_img = Image.open(args.image_path).convert("RGB")
+    input_img = T.Compose([
+        T.Resize(224),
+        T.ToTensor()
+    ])(input_img).unsqueeze(0).to(device)
+
+    # network configurations (ref inversion.py:21-25)
+    net = skip(args.input_depth, 3, num_channels_down=[16, 32, 64, 128, 128, 128],
+               num_channels_up=[16, 32, 64, 128, 128, 128],
+               num_channels_skip=[4, 4, 4, 4, 4, 4],
+               filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3],
+               downsample_mode='stride', pad='reflection').to(device)
+    net_input_saved = torch.randn((1, args.input_depth, input_img.shape[-2], input_img.shape[-1])).to(device)
+
+    # define the extractor
+    dino_preprocess = T.Compose([
+        T.Resize(224),
+        T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    ])
+    vit_extractor = VitExtractor(args.dino_model_name, device, state_dict=vit_state_dict)
+
+    def extract_feature(x):
+        if args.feature == 'cls':
+            f = vit_extractor.get_feature_from_input(dino_preprocess(x))[args.layer][:, 0, :]
+        elif args.feature == 'keys':
+            f = vit_extractor.get_keys_from_input(dino_preprocess(x), args.layer)
+        else:
+            raise ValueError('feature {} not supported.'.format(args.feature))
+        return f
+
+    # calculate the target feature from the input image
+    with torch.no_grad():
+        ref_feature = extract_feature(input_img)
+
+    # optimization configurations
+    optimizer = torch.optim.Adam(net.parameters(), lr=args.LR)
+    criterion = torch.nn.MSELoss()
+
+    # inversion loop
+    losses = []
+    for i in range(args.n_iter):
+        net_input = net_input_saved
+        if args.feature == 'cls':
+            # noise added to the input at each step as a regularization (ref inversion.py:56-62)
+            noise = (torch.randn(net_input_saved.shape, device=device) if noise_on_device
+                     else torch.randn(net_input_saved.shape).to(device))
+            if i < args.reduce_noise_stage_1_iter:
+                net_input = net_input_saved + (noise * 10)
+            elif i < args.reduce_noise_stage_2_iter:
+                net_input = net_input_saved + (noise * 2)
+            else:
+                net_input = net_input_saved + (noise * 0.5)
+
+        optimizer.zero_grad()
+        current_feature = extract_feature(net(net_input))
+
+        loss = criterion(current_feature, ref_feature)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.detach())
+        if callback is not None:
+            callback(i, losses[-1], net, net_input)
+
+        if i % args.log_freq == 0:
+            with torch.no_grad():   # the reference runs this extra forward with autograd on and drops the graph
+                result_img = net(net_input)[0].detach().cpu().clone()
+            result_img = T.ToPILImage()(result_img)
+            result_img.save(args.save_path)
+    return net, torch.stack(losses).cpu() if losses else torch.empty(0)
+
+
+def build_parser() -> ArgumentParser:
+    parser = ArgumentParser()
+    parser.add_argument("--feature", type=str, help='DINO-ViT feature to invert. options: cls | keys')
+    parser.add_argument("--layer", type=int, default=11,
+                        help='Transformer layer from which to extract the feature, between 0-11')
+    parser.add_argument("--dino_model_name", type=str, default='dino_vitb8')
+    parser.add_argument("--image_path", type=str, default='datasets/feature_visualization/limes.jpeg',
+                        help='path to the image to be used for the inversion.')
+    parser.add_argument("--save_path", type=str, required=True, help='path to save the result.')
+    parser.add_argument("--log_freq", type=int, default=100)
+    parser.add_argument("--input_depth", type=int, default=32)
+    parser.add_argument("--LR", type=float, default=0.01)
+    parser.add_argument("--n_iter", type=int, default=20000)
+    parser.add_argument("--reduce_noise_stage_1_iter", type=int, default=10000)
+    parser.add_argument("--reduce_noise_stage_2_iter", type=int, default=15000)
+    return parser
+
+
+if __name__ == '__main__':
+    invert(build_parser().parse_args())

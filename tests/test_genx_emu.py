@@ -132,3 +132,65 @@ def test_unsupported_configurations_are_refused():
         skip(3, 3, filter_size_down=9)
     with pytest.raises(NotImplementedError):
         skip(3, 3, downsample_mode='avg')
+
+
+# ---- against the reference's own builder (golden made by oracle/make_golden_inversion.py from /root/reference) ------------
+def _load_inversion_golden():
+    return torch.load(ROOT / "tests" / "golden" / "inversion_gen.pt", weights_only=False)
+
+
+def _close(fp, t, rel):
+    f = t.detach().reshape(-1).double()
+    idx = torch.linspace(0, f.numel() - 1, min(16, f.numel())).long()
+    tol = rel * max(fp["abs"] / max(f.numel(), 1), 1e-6)
+    return (tuple(t.shape) == tuple(fp["shape"]) and abs(f.sum().item() - fp["sum"]) <= rel * max(fp["abs"], 1e-6)
+            and (f[idx] - fp["samples"]).abs().max().item() <= 50 * tol)
+
+
+def test_inversion_tree_and_init_match_reference():
+    """Same state_dict keys (module naming incl. the ReflectionPad2d children), same shapes and - under the same seed - the same
+    default initialisation as the reference's skip() (construction order = RNG order)."""
+    from oracle.make_golden_inversion import INVERSION_ARGS
+    from splice_b200.models.unet.skip import skip
+
+    gold = _load_inversion_golden()
+    torch.manual_seed(0)
+    net = skip(32, 3, **INVERSION_ARGS)
+    sd = net.state_dict()
+    assert list(sd.keys()) == gold["keys"]
+    for k, v in sd.items():
+        fp = gold["init"][k]
+        f = v.reshape(-1).double()
+        idx = torch.linspace(0, f.numel() - 1, min(16, f.numel())).long()
+        assert tuple(v.shape) == tuple(fp["shape"]) and torch.equal(f[idx], fp["samples"]) and f.sum().item() == fp["sum"], k
+
+
+def test_inversion_engine_matches_reference_golden(emu_backend):
+    """The (emulated) engine on the golden input: output against the reference's own y, every parameter gradient and BatchNorm
+    buffer against the reference's fingerprints (tolerances: float32 through 36 BatchNorm layers, see tools/genx_compare.py)."""
+    from oracle.make_golden_inversion import INVERSION_ARGS, golden_input, perturb
+    from splice_b200.models.unet.skip import skip
+
+    gold = _load_inversion_golden()
+    torch.manual_seed(0)
+    net = skip(32, 3, **INVERSION_ARGS)
+    perturb(net, 1)
+    x, w = golden_input()
+    y = net(x)
+    assert (y - gold["y"]).abs().max().item() < 5e-4
+    (y * w).sum().backward()
+    # conv biases in front of a BatchNorm have an exactly-zero gradient (both sides return cancellation noise for them)
+    numel = {k: p.numel() for k, p in net.named_parameters()}
+    big = max(fp["abs"] / numel[k] for k, fp in gold["grads"].items())
+    bad = []
+    for k, p in net.named_parameters():
+        fp = gold["grads"][k]
+        if fp["abs"] / numel[k] < 1e-4 * big:
+            ok = p.grad.abs().mean().item() < 1e-3 * big
+        else:
+            ok = _close(fp, p.grad, 5e-2)
+        if not ok:
+            bad.append(k)
+    assert not bad, bad
+    bad = [k for k, v in net.state_dict().items() if k in gold["buffers"] and not _close(gold["buffers"][k], v.float(), 1e-3)]
+    assert not bad, bad

@@ -1342,6 +1342,22 @@ def _generator_exact_case(H, W):
 
 
 @check
+def generator_inversion_variant():
+    """inversion.py's generator (6 scales, 32-channel noise input, 7x7 / 5x5 / 3x3 filters, reflection padding) on
+    the generalised native engine (csrc/generator_x.cu) through skip() / NativeSkipX:
+      (a) against the golden the UNMODIFIED reference produced (tests/golden/inversion_gen.pt, oracle/make_golden_inversion.py):
+          output 5e-4 abs, parameter-gradient / BatchNorm-buffer fingerprints;
+      (b) against torch evaluating the same module tree in float64, torch's own float32 (cuDNN, TF32 off) as the yardstick
+          (tools/genx_compare.py), at 67x90 (odd, non-square) and at inversion.py's real size 224x298;
+      (c) six Adam iterations (graph capture on the 2nd, replay from the 3rd) against the torch-module copy of the same loop;
+      (d) splice_b200.inversion.invert() end to end for both feature kinds on a synthetic image (stand-in ViT-S/16 weights)."""
+    _oracle_on_gpu()
+    from tools import genx_gpu_check
+
+    return genx_gpu_check.run_all()
+
+
+@check
 def generator_native_small():
     return [_generator_case(1, 64, 64), _generator_case(1, 121, 117), _generator_case(2, 50, 70),
             _generator_exact_case(64, 64), _generator_exact_case(120, 117)]
