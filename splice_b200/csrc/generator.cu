@@ -165,57 +165,6 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_fwd_kernel(const float* __r
     }
 }
 
-// split-K epilogue: y = bias + sum of partials, per-block statistics of the result and (last block of a channel) the
-// BatchNorm constants. grid (ceil(N*HW / 1024), C): 256 threads x 4 pixels of one channel
-__global__ void __launch_bounds__(256) conv_finish_stats_kernel(const float* __restrict__ part, int splitK, const float* __restrict__ bias,
-                                                                float* __restrict__ y, int N, int C, int HW,
-                                                                float* __restrict__ stats_part, BnFin fin) {
-    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
-    __shared__ float red[8];
-    __shared__ int s_flag;
-    const int c = blockIdx.y, count = N * HW;
-    const size_t total = (size_t)N * C * HW;
-    const float b = bias[c];
-    float v[4];
-    bool ok[4];
-    float a[1] = {0.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int e = blockIdx.x * 1024 + i * 256 + threadIdx.x;
-        ok[i] = e < count;
-        v[i] = 0.f;
-        if (ok[i]) {
-            const size_t idx = ((size_t)(e / HW) * C + c) * HW + (e % HW);
-            float acc = b;
-            int k = 0;
-            for (; k + 4 <= splitK; k += 4) {
-                const float p0 = part[(size_t)k * total + idx], p1 = part[(size_t)(k + 1) * total + idx];
-                const float p2 = part[(size_t)(k + 2) * total + idx], p3 = part[(size_t)(k + 3) * total + idx];
-                acc += p0; acc += p1; acc += p2; acc += p3;
-            }
-            for (; k < splitK; ++k) acc += part[(size_t)k * total + idx];
-            y[idx] = acc;
-            v[i] = acc;
-            a[0] += acc;
-        }
-    }
-    block_reduce_vec<1>(a, red);
-    const int nb = min(1024, count - (int)blockIdx.x * 1024);
-    const float mean = a[0] / nb;
-    a[0] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float d = v[i] - mean;
-        a[0] += ok[i] ? d * d : 0.f;
-    }
-    block_reduce_vec<1>(a, red);
-    if (threadIdx.x == 0) {
-        float* o = stats_part + ((size_t)blockIdx.x * C + c) * 3;
-        o[0] = (float)nb; o[1] = mean; o[2] = a[0];
-    }
-    bn_finish_if_last(stats_part, gridDim.x, C, c, 1, c, gridDim.x, fin, &s_flag);
-}
-
 // nn.BatchNorm2d's running statistics (momentum 0.1, unbiased variance, num_batches_tracked) from the batch statistics
 // a forward pass left in its slot. A separate launch so that netG calls issued on parallel streams can apply their
 // updates afterwards in call order, as the reference's sequential calls do (they never influence outputs: the
@@ -311,16 +260,6 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_dgrad_kernel(const float* _
             float* q = o + ((size_t)(n * Cin + ci0 + ci) * Hin + iy) * Win + ix;
             *q = (accumulate && splitK == 1) ? *q + acc[ci] : acc[ci];
         }
-}
-// dst (=|+=) sum over the split partials
-__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splitK, size_t total,
-                                                           float* __restrict__ dst, int accumulate) {
-    pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
-    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        float v = accumulate ? dst[i] : 0.f;
-        for (int k = 0; k < splitK; ++k) v += part[(size_t)k * total + i];
-        dst[i] = v;
-    }
 }
 
 // partial weight / bias gradients over a strided subset of the spatial tiles.

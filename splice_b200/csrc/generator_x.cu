@@ -34,6 +34,8 @@ namespace splice {
 static constexpr int XCONV_THREADS = 128;
 static constexpr int XDYP = 20;                       // padded row of the pixel-major dy tile: 16 channels + 4
 static constexpr size_t XWGRAD_FLOATS = 8u << 20;     // scratch for weight-gradient partials (floats)
+static constexpr size_t XSPLIT_FLOATS = 4u << 20;     // scratch for the partial sums of split reductions (main stream)
+static constexpr size_t XSPLIT_SKIP_FLOATS = 1u << 18;   // same for the skip-branch convolutions on the side stream
 
 // nn.ReflectionPad2d index map: -1 -> 1, n -> n - 2 (identity inside [0, n))
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
@@ -42,13 +44,14 @@ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (
 // forward convolution, K x K, stride S, zero or reflection padding of (K-1)/2
 //   (+ producer BN/LeakyReLU on load, + bias, + optional sigmoid, + output statistics and BatchNorm constants)
 //   one thread per output pixel (linear over N*Ho*Wo), CO_T output channels per thread; taps from global / L1 one filter
-//   row at a time, weights of CI_C input channels staged in shared memory.
+//   row at a time, weights of CI_C input channels staged in shared memory. Low-resolution layers whose grids would not fill
+//   148 SMs split the input channels over blockIdx.z (partials folded by conv_finish_stats_kernel).
 // -------------------------------------------------------------------------------------------------
 template <int K, int S, int CO_T>
 static __global__ void __launch_bounds__(XCONV_THREADS)
 convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, InTf tf, const float* __restrict__ Wt,
                  const float* __restrict__ bias, int Cout, float* __restrict__ y, int Ho, int Wo, int reflect, int out_sigmoid,
-                 float* __restrict__ stats_part, BnFin fin) {
+                 float* __restrict__ stats_part, int splitK, BnFin fin) {
     pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     constexpr int CI_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2;
     __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
@@ -61,6 +64,8 @@ convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, 
     const int n = active ? p / (Ho * Wo) : 0, rem = active ? p % (Ho * Wo) : 0;
     const int oy = rem / Wo, ox = rem % Wo;
     const int co0 = blockIdx.y * CO_T;
+    const int cps = (Cin + splitK - 1) / splitK;                       // input channels of this split (blockIdx.z)
+    const int c_begin = blockIdx.z * cps, c_end = min(Cin, c_begin + cps);
     const int iy0 = oy * S - PAD, ix0 = ox * S - PAD;
     // taps are loaded unconditionally from in-image coordinates (reflected, or clamped and masked afterwards)
     int yoff[K], xoff[K];
@@ -84,8 +89,8 @@ convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, 
     const size_t plane = (size_t)Hin * Win;
     const float* xn = x + (size_t)n * Cin * plane;
 
-    for (int c0 = 0; c0 < Cin; c0 += CI_C) {
-        const int cn = min(CI_C, Cin - c0);
+    for (int c0 = c_begin; c0 < c_end; c0 += CI_C) {
+        const int cn = min(CI_C, c_end - c0);
         for (int idx = threadIdx.x; idx < CI_C * KK * CO_T; idx += XCONV_THREADS) {
             const int co = idx % CO_T, kk = (idx / CO_T) % KK, ci = idx / (CO_T * KK);
             s_w[ci][kk][co] = (ci < cn && co0 + co < Cout) ? Wt[((size_t)(co0 + co) * Cin + c0 + ci) * KK + kk] : 0.f;
@@ -118,6 +123,15 @@ convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, 
             }
         }
         __syncthreads();
+    }
+    if (splitK > 1) {   // partial sums; conv_finish_stats_kernel adds the bias and does the statistics
+        if (active) {
+            float* o = y + (size_t)blockIdx.z * ((size_t)N * Cout * Ho * Wo);
+#pragma unroll
+            for (int co = 0; co < CO_T; ++co)
+                if (co0 + co < Cout) o[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = acc[co];
+        }
+        return;
     }
 #pragma unroll
     for (int co = 0; co < CO_T; ++co) {
@@ -171,7 +185,7 @@ convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, 
 template <int K, int S, int CI_T>
 static __global__ void __launch_bounds__(XCONV_THREADS)
 convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo, const float* __restrict__ Wt, int Cin,
-                   float* __restrict__ dXq, int Hq, int Wq, int ext, int accumulate) {
+                   float* __restrict__ dXq, int Hq, int Wq, int ext, int accumulate, int splitK) {
     pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
     constexpr int CO_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2;
     __shared__ __align__(16) float s_w[CO_C][KK][CI_T];
@@ -181,6 +195,8 @@ convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo
     const int n = active ? p / (Hq * Wq) : 0, rem = active ? p % (Hq * Wq) : 0;
     const int qy = rem / Wq, qx = rem % Wq;
     const int ci0 = blockIdx.y * CI_T;
+    const int cps = (Cout + splitK - 1) / splitK;                      // output channels of this split (blockIdx.z)
+    const int c_begin = blockIdx.z * cps, c_end = min(Cout, c_begin + cps);
     // taps: output row / column reached through tap k (0 when there is none, so that loads are unconditional) + validity
     int yoff[K], xoff[K];
     bool rok[K], cok[K];
@@ -197,8 +213,8 @@ convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo
     for (int i = 0; i < CI_T; ++i) acc[i] = 0.f;
     const size_t plane = (size_t)Ho * Wo;
     const float* dyn = dy + (size_t)n * Cout * plane;
-    for (int c0 = 0; c0 < Cout; c0 += CO_C) {
-        const int cn = min(CO_C, Cout - c0);
+    for (int c0 = c_begin; c0 < c_end; c0 += CO_C) {
+        const int cn = min(CO_C, c_end - c0);
         for (int idx = threadIdx.x; idx < CO_C * KK * CI_T; idx += XCONV_THREADS) {
             const int ci = idx % CI_T, kk = (idx / CI_T) % KK, co = idx / (CI_T * KK);
             s_w[co][kk][ci] = (co < cn && ci0 + ci < Cin) ? Wt[((size_t)(c0 + co) * Cin + ci0 + ci) * KK + kk] : 0.f;
@@ -222,11 +238,12 @@ convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo
         __syncthreads();
     }
     if (!active) return;
+    float* o = dXq + (splitK > 1 ? (size_t)blockIdx.z * ((size_t)N * Cin * Hq * Wq) : 0);   // split: partials for sum_partials_kernel
 #pragma unroll
     for (int ci = 0; ci < CI_T; ++ci)
         if (ci0 + ci < Cin) {
-            float* q = dXq + ((size_t)(n * Cin + ci0 + ci) * Hq + qy) * Wq + qx;
-            *q = accumulate ? *q + acc[ci] : acc[ci];
+            float* q = o + ((size_t)(n * Cin + ci0 + ci) * Hq + qy) * Wq + qx;
+            *q = (accumulate && splitK == 1) ? *q + acc[ci] : acc[ci];
         }
 }
 
@@ -402,34 +419,68 @@ static inline int elementwise_blocks(size_t total, int per_sm) {
         else { set_error("generator: unsupported conv k=%d stride=%d", K, S); return SPLICE_ERR_UNSUPPORTED; } \
     } while (0)
 
+// Split factor of a layer's reduction channels: grids that would not fill 148 SMs twice over (low-resolution layers: a few hundred
+// pixels x 128 channels) are widened by splitting the reduction, at least 8 channels per split, partials within `cap` floats.
+static constexpr int XTARGET_BLOCKS = 296;
+static int pick_split(int P, int c_fast, int ct, int c_slow, size_t out_elems, size_t cap) {
+    const int blocks = ceil_div(P, XCONV_THREADS) * ceil_div(c_fast, ct);
+    if (blocks >= XTARGET_BLOCKS || P > 16384) return 1;
+    int sk = ceil_div(XTARGET_BLOCKS, blocks);
+    const int max_sk = c_slow / 8 > 0 ? c_slow / 8 : 1;
+    if (sk > max_sk) sk = max_sk;
+    if (sk > 16) sk = 16;
+    while (sk > 1 && (size_t)sk * out_elems > cap) --sk;
+    return sk;
+}
+
+// split / split_cap: scratch for the partial sums of a split reduction (floats); only layers with a BatchNorm epilogue split
 static int launch_convx_fwd(int K, int S, const float* x, int N, int Cin, int Hin, int Win, InTf tf, const float* Wt, const float* bias,
-                            int Cout, float* y, int Ho, int Wo, int reflect, int sigmoid, float* stats_part, BnFin fin, cudaStream_t st) {
+                            int Cout, float* y, int Ho, int Wo, int reflect, int sigmoid, float* stats_part, BnFin fin, float* split,
+                            size_t split_cap, cudaStream_t st) {
     const int ct = chan_tile(Cout);
-    dim3 grid(ceil_div(N * Ho * Wo, XCONV_THREADS), ceil_div(Cout, ct), 1);
-#define XF(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(convx_fwd_kernel<KK, SS, CT>, grid, dim3(XCONV_THREADS), 0, st, x, N, Cin, Hin, Win, tf, Wt, bias, Cout, y, Ho, Wo, reflect, sigmoid, stats_part, fin))
+    const size_t out_elems = (size_t)N * Cout * Ho * Wo;
+    const int sk = (fin.konst && split) ? pick_split(N * Ho * Wo, Cout, ct, Cin, out_elems, split_cap) : 1;
+    dim3 grid(ceil_div(N * Ho * Wo, XCONV_THREADS), ceil_div(Cout, ct), sk);
+    float* dst = sk > 1 ? split : y;
+    float* stats = sk > 1 ? nullptr : stats_part;
+    BnFin fin_conv = fin;
+    if (sk > 1) fin_conv.konst = nullptr;   // the split epilogue kernel does the statistics
+#define XF(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(convx_fwd_kernel<KK, SS, CT>, grid, dim3(XCONV_THREADS), 0, st, x, N, Cin, Hin, Win, tf, Wt, bias, Cout, dst, Ho, Wo, reflect, sigmoid, stats, sk, fin_conv))
 #define XF3(KK, SS) do { if (ct == 4) XF(KK, SS, 4); else if (ct == 8) XF(KK, SS, 8); else XF(KK, SS, 16); } while (0)
     XDISPATCH_KS(XF3);
 #undef XF3
 #undef XF
     SPLICE_LAUNCH_CHECK();
+    if (sk > 1) {
+        dim3 fgrid(ceil_div(N * Ho * Wo, 1024), Cout);
+        SPLICE_CHECK_CUDA(launch_pdl(conv_finish_stats_kernel, fgrid, dim3(256), 0, st, (const float*)split, sk, bias, y, N, Cout, Ho * Wo, stats_part, fin));
+        SPLICE_LAUNCH_CHECK();
+    }
     return SPLICE_OK;
 }
 
 // d(transformed conv input) [N,Cin,Hin,Win] (=|+=) from dy [N,Cout,Ho,Wo]; dpad: scratch for the padded domain (reflection)
 static int launch_convx_dgrad(int K, int S, const float* dy, int N, int Cout, int Ho, int Wo, const float* Wt, int Cin, float* dX, int Hin,
-                              int Win, int reflect, int accumulate, float* dpad, cudaStream_t st) {
+                              int Win, int reflect, int accumulate, float* dpad, float* split, size_t split_cap, cudaStream_t st) {
     const int ext = (reflect && K > 1) ? (K - 1) / 2 : 0;
     const int Hq = Hin + 2 * ext, Wq = Win + 2 * ext;
-    float* dst = ext ? dpad : dX;
+    float* dst = ext ? dpad : dX;                       // where the (summed) data gradient of the domain goes
     const int acc_k = ext ? 0 : accumulate;
     const int ct = chan_tile(Cin);
-    dim3 grid(ceil_div(N * Hq * Wq, XCONV_THREADS), ceil_div(Cin, ct), 1);
-#define XD(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(convx_dgrad_kernel<KK, SS, CT>, grid, dim3(XCONV_THREADS), 0, st, dy, N, Cout, Ho, Wo, Wt, Cin, dst, Hq, Wq, ext, acc_k))
+    const size_t total_q = (size_t)N * Cin * Hq * Wq;
+    const int sk = pick_split(N * Hq * Wq, Cin, ct, Cout, total_q, split_cap);
+    dim3 grid(ceil_div(N * Hq * Wq, XCONV_THREADS), ceil_div(Cin, ct), sk);
+    float* kdst = sk > 1 ? split : dst;
+#define XD(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(convx_dgrad_kernel<KK, SS, CT>, grid, dim3(XCONV_THREADS), 0, st, dy, N, Cout, Ho, Wo, Wt, Cin, kdst, Hq, Wq, ext, acc_k, sk))
 #define XD3(KK, SS) do { if (ct == 4) XD(KK, SS, 4); else if (ct == 8) XD(KK, SS, 8); else XD(KK, SS, 16); } while (0)
     XDISPATCH_KS(XD3);
 #undef XD3
 #undef XD
     SPLICE_LAUNCH_CHECK();
+    if (sk > 1) {
+        SPLICE_CHECK_CUDA(launch_pdl(sum_partials_kernel, dim3(elementwise_blocks(total_q, 8)), dim3(256), 0, st, (const float*)split, sk, total_q, dst, acc_k));
+        SPLICE_LAUNCH_CHECK();
+    }
     if (ext) {
         const size_t total = (size_t)N * Cin * Hin * Win;
         SPLICE_CHECK_CUDA(launch_pdl(reflect_fold_kernel, dim3(elementwise_blocks(total, 8)), dim3(256), 0, st, (const float*)dpad, Hin, Win, ext,
@@ -626,12 +677,13 @@ int GenXEngine::configure(int N, int H, int W) {
     dout_copy_ = (float*)nx();
     bstat_ = (float2*)nx();
 
-    // scratch = [statistics partials | skip-branch statistics partials | weight-gradient partials | padded data gradient]
+    // scratch = [statistics partials | skip-branch statistics partials | split partial sums | skip-branch split partial sums |
+    //            weight-gradient partials | padded data gradient]
     const size_t conv_blocks = (size_t)ceil_div(N * H * W, XCONV_THREADS);
     stats_floats_ = (conv_blocks + (size_t)N * ceil_div(H, TH) * ceil_div(W, TW)) * max_c_ * 3;
     skip_floats_ = conv_blocks * max_cskip_ * 3;
     dpad_floats_ = dpad;
-    const size_t bytes = (stats_floats_ + skip_floats_ + XWGRAD_FLOATS + dpad_floats_) * sizeof(float) + 4096;
+    const size_t bytes = (stats_floats_ + skip_floats_ + XSPLIT_FLOATS + XSPLIT_SKIP_FLOATS + XWGRAD_FLOATS + dpad_floats_) * sizeof(float) + 4096;
     if (bytes > scratch_bytes_) {
         SPLICE_CHECK_CUDA(cudaDeviceSynchronize());
         cudaFree(scratch_);
@@ -695,6 +747,8 @@ int GenXEngine::forward_body(cudaStream_t st) {
     const int N = N_, H = H_, W = W_, refl = cfg_.reflect;
     float* part = static_cast<float*>(scratch_);
     float* part_skip = part + stats_floats_;
+    float* split = part_skip + skip_floats_;
+    float* split_skip = split + XSPLIT_FLOATS;
     const float eps = 1e-5f;
 
     auto bn_fin = [&](const Bn& b, float4* k) {
@@ -702,8 +756,9 @@ int GenXEngine::forward_body(cudaStream_t st) {
     };
     auto conv_bn = [&](const Conv& c, const Bn& b, const float* in, int hin, int win, InTf tf, float* y, int ho, int wo, float4* k,
                        float* stats, cudaStream_t cs) -> int {
+        const bool on_side = cs == side_ && stats == part_skip;
         return launch_convx_fwd(c.k, c.stride, in, N, c.cin, hin, win, tf, param_[c.pw], param_[c.pb], c.cout, y, ho, wo, refl, 0, stats,
-                                bn_fin(b, k), cs);
+                                bn_fin(b, k), on_side ? split_skip : split, on_side ? XSPLIT_SKIP_FLOATS : XSPLIT_FLOATS, cs);
     };
 
     // down path. The skip convolutions only feed the concats of the up path: they run on the side stream (a parallel branch
@@ -742,7 +797,7 @@ int GenXEngine::forward_body(cudaStream_t st) {
         GRC(conv_bn(c.c2, c.bc2, b.c1_raw, th, tw, InTf{b.k_c1, 1}, b.c2_raw, th, tw, b.k_c2, part, st));
     }
     GRC(launch_convx_fwd(1, 1, sb_[0].c2_raw, N, final_.cin, H, W, InTf{sb_[0].k_c2, 1}, param_[final_.pw], param_[final_.pb], final_.cout, out_, H, W,
-                         0, cfg_.sigmoid ? 1 : 0, nullptr, BnFin{nullptr, nullptr, nullptr, nullptr, nullptr, eps}, st));
+                         0, cfg_.sigmoid ? 1 : 0, nullptr, BnFin{nullptr, nullptr, nullptr, nullptr, nullptr, eps}, nullptr, 0, st));
     return SPLICE_OK;
 }
 
@@ -768,7 +823,8 @@ int GenXEngine::backward_body(bool accumulate, cudaStream_t st) {
     const int N = N_, H = H_, W = W_, refl = cfg_.reflect;
     const int acc = accumulate ? 1 : 0;
     float* part = static_cast<float*>(scratch_);
-    float* wpart = part + stats_floats_ + skip_floats_;
+    float* split = part + stats_floats_ + skip_floats_;
+    float* wpart = split + XSPLIT_FLOATS + XSPLIT_SKIP_FLOATS;
     float* dpad = wpart + XWGRAD_FLOATS;
 
     // BatchNorm(+LeakyReLU) backward of one layer: afterwards dA holds d(raw conv output)
@@ -799,7 +855,8 @@ int GenXEngine::backward_body(bool accumulate, cudaStream_t st) {
         return launch_convx_wgrad(c.k, c.stride, in, N, c.cin, hin, win, tf, dy, c.cout, ho, wo, refl, wpart, grad_[c.pw], grad_[c.pb], acc, ws);
     };
     auto dgrad = [&](const Conv& c, const float* dy, int ho, int wo, float* dX, int hin, int win, int accumulate_dx) -> int {
-        return launch_convx_dgrad(c.k, c.stride, dy, N, c.cout, ho, wo, param_[c.pw], c.cin, dX, hin, win, refl, accumulate_dx, dpad, st);
+        return launch_convx_dgrad(c.k, c.stride, dy, N, c.cout, ho, wo, param_[c.pw], c.cin, dX, hin, win, refl, accumulate_dx, dpad, split, XSPLIT_FLOATS,
+                                  st);
     };
 
     // final 1x1 conv (+ sigmoid)
