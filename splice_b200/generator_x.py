@@ -212,6 +212,11 @@ class NativeSkipX(nn.Sequential):
                        "splice_genx_backward")
 
     def forward(self, input):
+        if torch.is_grad_enabled() and input.requires_grad:
+            # the engine stops at the parameter gradients (what inversion.py's optimiser consumes, inversion.py:50,68); returning
+            # None for d loss / d input silently would be a wrong answer, so say so
+            raise NotImplementedError("the native generator does not compute the gradient with respect to its input: pass "
+                                      "net_input.detach() (inversion.py optimises the network's parameters only)")
         anchor = next(self.parameters())
         keep = torch.is_grad_enabled() and anchor.requires_grad
         return _GenXFn.apply(anchor, self, keep, input)

@@ -68,7 +68,8 @@ def _tie_free_input(net, shape, first_seed, margin=2e-5):
 
 def test_inversion_variant_matches_torch_modules(emu_backend):
     """inversion.py:21-25's network (6 scales, 7x7 / 5x5 / 3x3, reflection padding, 32-channel noise input) at a small, odd,
-    non-square size: forward, every parameter gradient, running statistics; then a second iteration as the inversion loop runs it."""
+    non-square size: forward, every parameter gradient, running statistics (the loop's later iterations - zero_grad(), noise added
+    to the input, graph replay - are covered on the GPU by generator_inversion_variant's adam_loop part)."""
     from splice_b200.generator_x import NativeSkipX
     from splice_b200.models.unet.skip import skip
     from tools.genx_compare import compare, randomise
@@ -82,10 +83,8 @@ def test_inversion_variant_matches_torch_modules(emu_backend):
     randomise(net, 1)
     x = torch.randn(1, 32, 67, 90, generator=torch.Generator().manual_seed(2))
     compare(net, x, 3)
-    for p in net.parameters():      # optimizer.zero_grad() (inversion.py:64), then noise added to the input (inversion.py:57-62)
-        p.grad = None
-    x2 = x + 0.5 * torch.randn(x.shape, generator=torch.Generator().manual_seed(4))
-    compare(net, x2, 5)
+    with pytest.raises(NotImplementedError, match="gradient with respect to its input"):
+        net(x.clone().requires_grad_(True))
 
 
 @pytest.mark.parametrize("pad", ["zero", "reflection"])
