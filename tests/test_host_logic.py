@@ -270,3 +270,18 @@ def test_device_aug_feed_consumes_the_reference_random_stream(tmp_path):
     # the texture image is only flipped and cropped: exact
     for (sa, _, _), (sb, _, _) in zip(ref, got):
         assert torch.equal(sa["B_global"], sb["B_global"])
+
+
+def test_inversion_noise_feed_keeps_the_reference_stream():
+    """inversion.py:56-62 draws `torch.randn(shape)` inline every iteration; NoiseFeed draws the same tensors ahead on a worker
+    thread (same process-wide CPU generator, same order)."""
+    from splice_b200.inversion import NoiseFeed
+
+    shape = (1, 32, 20, 30)
+    torch.manual_seed(5)
+    want = [torch.randn(shape) for _ in range(6)]
+    torch.manual_seed(5)
+    feed = NoiseFeed(shape, 6, depth=2, pin=False)
+    got = [feed.next() for _ in range(6)]
+    feed.close()
+    assert all(torch.equal(a, b) for a, b in zip(want, got))

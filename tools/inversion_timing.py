@@ -43,7 +43,10 @@ from splice_b200 import inversion  # noqa: E402
 args = types.SimpleNamespace(feature=feature, layer=11, dino_model_name=model, image_path=f"{td}/in.png", save_path=f"{td}/out.png",
                              log_freq=10 ** 9, input_depth=32, LR=0.01, n_iter=n_iter, reduce_noise_stage_1_iter=10000,
                              reduce_noise_stage_2_iter=15000)
-for on_device in (False, True):
+variants = [("native_it_s", {})]
+if feature == "cls":   # the 'keys' mode adds no noise
+    variants += [("native_it_s_inline_cpu_noise", {"prefetch_noise": False}), ("native_it_s_noise_on_device", {"noise_on_device": True})]
+for key, kw in variants:
     events = []
 
     def cb(i, loss, net, net_input):
@@ -52,12 +55,9 @@ for on_device in (False, True):
         events.append(e)
 
     torch.manual_seed(0)
-    _, losses = inversion.invert(args, vit_state_dict=vsd, callback=cb, noise_on_device=on_device)
-    key = "native_it_s" + ("_noise_on_device" if on_device else "")
+    _, losses = inversion.invert(args, vit_state_dict=vsd, callback=cb, **kw)
     out[key] = it_per_s(events)
-    out["native_loss_first_last"] = [losses[0].item(), losses[-1].item()]
-    if feature != "cls":
-        break   # the 'keys' mode adds no noise
+    out[key.replace("it_s", "loss_first_last")] = [losses[0].item(), losses[-1].item()]
 
 # ---- stock PyTorch: the reference's loop with torch modules + the oracle ViT ---------------------------------
 from splice_b200.models.unet.skip import skip  # noqa: E402  (module tree only; evaluated by torch, not by the engine)
