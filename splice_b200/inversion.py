@@ -28,6 +28,13 @@ from .models.unet.skip import skip
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
+# network configuration of the script (ref inversion.py:21-25); the input depth comes from the command line (default 32)
+NET_ARGS = dict(num_channels_down=[16, 32, 64, 128, 128, 128],
+                num_channels_up=[16, 32, 64, 128, 128, 128],
+                num_channels_skip=[4, 4, 4, 4, 4, 4],
+                filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3],
+                downsample_mode='stride', pad='reflection')
+
 
 class NoiseFeed:
     """The per-iteration regularisation noise of the 'cls' mode (ref inversion.py:56-62: `torch.randn(shape).to(device)` inside
@@ -89,11 +96,7 @@ def invert(args, vit_state_dict=None, callback=None, noise_on_device=False, pref
     ])(input_img).unsqueeze(0).to(device)
 
     # network configurations (ref inversion.py:21-25)
-    net = skip(args.input_depth, 3, num_channels_down=[16, 32, 64, 128, 128, 128],
-               num_channels_up=[16, 32, 64, 128, 128, 128],
-               num_channels_skip=[4, 4, 4, 4, 4, 4],
-               filter_size_down=[7, 7, 5, 5, 3, 3], filter_size_up=[7, 7, 5, 5, 3, 3],
-               downsample_mode='stride', pad='reflection').to(device)
+    net = skip(args.input_depth, 3, **NET_ARGS).to(device)
     net_input_saved = torch.randn((1, args.input_depth, input_img.shape[-2], input_img.shape[-1])).to(device)
 
     # define the extractor

@@ -150,11 +150,13 @@ def test_inversion_tree_and_init_match_reference():
     """Same state_dict keys (module naming incl. the ReflectionPad2d children), same shapes and - under the same seed - the same
     default initialisation as the reference's skip() (construction order = RNG order)."""
     from oracle.make_golden_inversion import INVERSION_ARGS
+    from splice_b200.inversion import NET_ARGS
     from splice_b200.models.unet.skip import skip
 
+    assert NET_ARGS == INVERSION_ARGS      # what the package's inversion script builds == what the golden was made with
     gold = _load_inversion_golden()
     torch.manual_seed(0)
-    net = skip(32, 3, **INVERSION_ARGS)
+    net = skip(32, 3, **NET_ARGS)
     sd = net.state_dict()
     assert list(sd.keys()) == gold["keys"]
     for k, v in sd.items():

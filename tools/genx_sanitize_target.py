@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 import torch  # noqa: E402
 
-from oracle.make_golden_inversion import INVERSION_ARGS  # noqa: E402
+from splice_b200.inversion import NET_ARGS as INVERSION_ARGS  # noqa: E402
 from splice_b200.models.unet.skip import skip  # noqa: E402
 
 torch.manual_seed(0)
