@@ -47,45 +47,57 @@ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (
 //   row at a time, weights of CI_C input channels staged in shared memory. Low-resolution layers whose grids would not fill
 //   148 SMs split the input channels over blockIdx.z (partials folded by conv_finish_stats_kernel).
 // -------------------------------------------------------------------------------------------------
+// pixels per thread: the wide stride-1 filters (5x5, 7x7) give a thread two horizontally adjacent output pixels - a filter row is
+// then K + 1 loads for 2 K taps, and every shared-memory weight read feeds two FMAs per channel
+template <int K, int S>
+struct XPx { static constexpr int value = (S == 1 && K >= 5) ? 2 : 1; };
+
 template <int K, int S, int CO_T>
 static __global__ void __launch_bounds__(XCONV_THREADS)
 convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, InTf tf, const float* __restrict__ Wt,
                  const float* __restrict__ bias, int Cout, float* __restrict__ y, int Ho, int Wo, int reflect, int out_sigmoid,
                  float* __restrict__ stats_part, int splitK, BnFin fin) {
     pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
-    constexpr int CI_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2;
+    constexpr int CI_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2, PX = XPx<K, S>::value, NC = K + PX - 1;
     __shared__ __align__(16) float s_w[CI_C][KK][CO_T];
     __shared__ float2 s_ab[CI_C];
-    __shared__ float red[4 * CO_T];
+    __shared__ float red[4 * (CO_T + 1)];
     __shared__ int s_flag;
-    const int P = N * Ho * Wo;
+    const int Wg = (Wo + PX - 1) / PX;                                 // pixel groups per output row
+    const int P = N * Ho * Wg;
     const int p = blockIdx.x * XCONV_THREADS + threadIdx.x;
     const bool active = p < P;
-    const int n = active ? p / (Ho * Wo) : 0, rem = active ? p % (Ho * Wo) : 0;
-    const int oy = rem / Wo, ox = rem % Wo;
+    const int n = active ? p / (Ho * Wg) : 0, rem = active ? p % (Ho * Wg) : 0;
+    const int oy = rem / Wg, ox0 = (rem % Wg) * PX;
+    bool pok[PX];                                                      // which of this thread's pixels exist
+#pragma unroll
+    for (int j = 0; j < PX; ++j) pok[j] = active && ox0 + j < Wo;
     const int co0 = blockIdx.y * CO_T;
     const int cps = (Cin + splitK - 1) / splitK;                       // input channels of this split (blockIdx.z)
     const int c_begin = blockIdx.z * cps, c_end = min(Cin, c_begin + cps);
-    const int iy0 = oy * S - PAD, ix0 = ox * S - PAD;
+    const int iy0 = oy * S - PAD, ix0 = ox0 * S - PAD;
     // taps are loaded unconditionally from in-image coordinates (reflected, or clamped and masked afterwards)
-    int yoff[K], xoff[K];
-    bool rok[K], cok[K];
+    int yoff[K], xoff[NC];
+    bool rok[K], cok[NC];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        int iy = iy0 + k, ix = ix0 + k;
-        if (reflect) {
-            rok[k] = active; cok[k] = true;
-            iy = reflect_idx(iy, Hin); ix = reflect_idx(ix, Win);
-        } else {
-            rok[k] = active && iy >= 0 && iy < Hin;
-            cok[k] = ix >= 0 && ix < Win;
-        }
+        int iy = iy0 + k;
+        if (reflect) { rok[k] = true; iy = reflect_idx(iy, Hin); }
+        else rok[k] = iy >= 0 && iy < Hin;
         yoff[k] = min(max(iy, 0), Hin - 1) * Win;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        int ix = ix0 + k;
+        if (reflect) { cok[k] = true; ix = reflect_idx(ix, Win); }
+        else cok[k] = ix >= 0 && ix < Win;
         xoff[k] = min(max(ix, 0), Win - 1);
     }
-    float acc[CO_T];
+    float acc[PX][CO_T];
 #pragma unroll
-    for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+    for (int j = 0; j < PX; ++j)
+#pragma unroll
+        for (int i = 0; i < CO_T; ++i) acc[j][i] = 0.f;
     const size_t plane = (size_t)Hin * Win;
     const float* xn = x + (size_t)n * Cin * plane;
 
@@ -106,65 +118,91 @@ convx_fwd_kernel(const float* __restrict__ x, int N, int Cin, int Hin, int Win, 
             const float2 ab = s_ab[ci];
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                float row[K];
+                float row[NC];
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) row[kx] = __ldg(base + yoff[ky] + xoff[kx]);
+                for (int k = 0; k < NC; ++k) row[k] = __ldg(base + yoff[ky] + xoff[k]);
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    float v = row[kx];
+                for (int k = 0; k < NC; ++k) {
+                    float v = row[k];
                     if (tf.k) {
                         v = fmaf(ab.x, v, ab.y);
                         if (tf.lrelu) v = v < 0.f ? v * LRELU : v;
                     }
-                    v = (rok[ky] && cok[kx]) ? v : 0.f;   // zero padding lives in the post-BN/activation domain
-#pragma unroll
-                    for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v, s_w[ci][ky * K + kx][co], acc[co]);
+                    row[k] = (rok[ky] && cok[k]) ? v : 0.f;   // zero padding lives in the post-BN/activation domain
                 }
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                    for (int co = 0; co < CO_T; ++co) {
+                        const float wv = s_w[ci][ky * K + kx][co];
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) acc[j][co] = fmaf(row[kx + j], wv, acc[j][co]);
+                    }
             }
         }
         __syncthreads();
     }
     if (splitK > 1) {   // partial sums; conv_finish_stats_kernel adds the bias and does the statistics
-        if (active) {
-            float* o = y + (size_t)blockIdx.z * ((size_t)N * Cout * Ho * Wo);
+        float* o = y + (size_t)blockIdx.z * ((size_t)N * Cout * Ho * Wo);
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
 #pragma unroll
             for (int co = 0; co < CO_T; ++co)
-                if (co0 + co < Cout) o[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = acc[co];
-        }
+                if (pok[j] && co0 + co < Cout) o[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox0 + j] = acc[j][co];
         return;
     }
 #pragma unroll
     for (int co = 0; co < CO_T; ++co) {
         if (co0 + co < Cout) {
-            float v = acc[co] + bias[co0 + co];
-            if (out_sigmoid) v = 1.f / (1.f + __expf(-v));
-            acc[co] = v;
-            if (active) y[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox] = v;
+            const float b = bias[co0 + co];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                float v = acc[j][co] + b;
+                if (out_sigmoid) v = 1.f / (1.f + __expf(-v));
+                acc[j][co] = v;
+                if (pok[j]) y[((size_t)(n * Cout + co0 + co) * Ho + oy) * Wo + ox0 + j] = v;
+            }
         }
     }
     if (stats_part) {
         // per-block (count, mean, M2) of each output channel: two block reductions, centred second pass
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const float cnt = (float)min(XCONV_THREADS, P - (int)blockIdx.x * XCONV_THREADS);
+        float mine = 0.f;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) mine += pok[j] ? 1.f : 0.f;
+        {
+            const float sv = warp_sum(mine);
+            if (lane == 0) red[w * (CO_T + 1) + CO_T] = sv;
+        }
         float mean[CO_T], m2[CO_T];
 #pragma unroll
         for (int co = 0; co < CO_T; ++co) {
-            const float sv = warp_sum(active ? acc[co] : 0.f);
-            if (lane == 0) red[w * CO_T + co] = sv;
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) t += pok[j] ? acc[j][co] : 0.f;
+            const float sv = warp_sum(t);
+            if (lane == 0) red[w * (CO_T + 1) + co] = sv;
         }
         __syncthreads();
+        const float cnt = red[CO_T] + red[(CO_T + 1) + CO_T] + red[2 * (CO_T + 1) + CO_T] + red[3 * (CO_T + 1) + CO_T];
 #pragma unroll
-        for (int co = 0; co < CO_T; ++co) mean[co] = (red[co] + red[CO_T + co] + red[2 * CO_T + co] + red[3 * CO_T + co]) / cnt;
+        for (int co = 0; co < CO_T; ++co)
+            mean[co] = (red[co] + red[(CO_T + 1) + co] + red[2 * (CO_T + 1) + co] + red[3 * (CO_T + 1) + co]) / cnt;
         __syncthreads();
 #pragma unroll
         for (int co = 0; co < CO_T; ++co) {
-            const float d = acc[co] - mean[co];
-            const float sv = warp_sum(active ? d * d : 0.f);
-            if (lane == 0) red[w * CO_T + co] = sv;
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const float d = acc[j][co] - mean[co];
+                t += pok[j] ? d * d : 0.f;
+            }
+            const float sv = warp_sum(t);
+            if (lane == 0) red[w * (CO_T + 1) + co] = sv;
         }
         __syncthreads();
 #pragma unroll
-        for (int co = 0; co < CO_T; ++co) m2[co] = red[co] + red[CO_T + co] + red[2 * CO_T + co] + red[3 * CO_T + co];
+        for (int co = 0; co < CO_T; ++co) m2[co] = red[co] + red[(CO_T + 1) + co] + red[2 * (CO_T + 1) + co] + red[3 * (CO_T + 1) + co];
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int co = 0; co < CO_T; ++co)
@@ -187,30 +225,39 @@ static __global__ void __launch_bounds__(XCONV_THREADS)
 convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo, const float* __restrict__ Wt, int Cin,
                    float* __restrict__ dXq, int Hq, int Wq, int ext, int accumulate, int splitK) {
     pdl_sync();   // programmatic dependent launch: scheduled under the previous kernel's tail, waits for its completion here
-    constexpr int CO_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2;
+    constexpr int CO_C = (K >= 5 ? 4 : 8), KK = K * K, PAD = (K - 1) / 2, PX = XPx<K, S>::value, NC = K + PX - 1;
     __shared__ __align__(16) float s_w[CO_C][KK][CI_T];
-    const int P = N * Hq * Wq;
+    const int Wg = (Wq + PX - 1) / PX;                                 // pixel groups per domain row
+    const int P = N * Hq * Wg;
     const int p = blockIdx.x * XCONV_THREADS + threadIdx.x;
     const bool active = p < P;
-    const int n = active ? p / (Hq * Wq) : 0, rem = active ? p % (Hq * Wq) : 0;
-    const int qy = rem / Wq, qx = rem % Wq;
+    const int n = active ? p / (Hq * Wg) : 0, rem = active ? p % (Hq * Wg) : 0;
+    const int qy = rem / Wg, qx0 = (rem % Wg) * PX;
     const int ci0 = blockIdx.y * CI_T;
     const int cps = (Cout + splitK - 1) / splitK;                      // output channels of this split (blockIdx.z)
     const int c_begin = blockIdx.z * cps, c_end = min(Cout, c_begin + cps);
-    // taps: output row / column reached through tap k (0 when there is none, so that loads are unconditional) + validity
-    int yoff[K], xoff[K];
-    bool rok[K], cok[K];
+    // rows: output row reached through tap ky. columns: pixel j of the thread meets tap kx in column tx = qx0 + j - ext + PAD - kx
+    // of dy; the PX pixels together touch NC = K + PX - 1 distinct columns, indexed c = K - 1 - kx + j (PX > 1 only for S = 1).
+    // Indices are 0 where there is no such output (loads stay unconditional), validity is kept beside them.
+    int yoff[K], xoff[NC];
+    bool rok[K], cok[NC];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int ty = qy - ext + PAD - k, tx = qx - ext + PAD - k;
-        rok[k] = active && ty >= 0 && ty % S == 0 && ty / S < Ho;
-        cok[k] = tx >= 0 && tx % S == 0 && tx / S < Wo;
+        const int ty = qy - ext + PAD - k;
+        rok[k] = ty >= 0 && ty % S == 0 && ty / S < Ho;
         yoff[k] = (rok[k] ? ty / S : 0) * Wo;
-        xoff[k] = cok[k] ? tx / S : 0;
     }
-    float acc[CI_T];
 #pragma unroll
-    for (int i = 0; i < CI_T; ++i) acc[i] = 0.f;
+    for (int c = 0; c < NC; ++c) {
+        const int tx = qx0 - ext + PAD - (K - 1) + c;
+        cok[c] = tx >= 0 && tx % S == 0 && tx / S < Wo;
+        xoff[c] = cok[c] ? tx / S : 0;
+    }
+    float acc[PX][CI_T];
+#pragma unroll
+    for (int j = 0; j < PX; ++j)
+#pragma unroll
+        for (int i = 0; i < CI_T; ++i) acc[j][i] = 0.f;
     const size_t plane = (size_t)Ho * Wo;
     const float* dyn = dy + (size_t)n * Cout * plane;
     for (int c0 = c_begin; c0 < c_end; c0 += CO_C) {
@@ -224,15 +271,19 @@ convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo
             const float* base = dyn + (size_t)(c0 + co) * plane;
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                float row[K];
+                float row[NC];
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) row[kx] = __ldg(base + yoff[ky] + xoff[kx]);
+                for (int c = 0; c < NC; ++c) row[c] = __ldg(base + yoff[ky] + xoff[c]);
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    const float v = (rok[ky] && cok[kx]) ? row[kx] : 0.f;
+                for (int c = 0; c < NC; ++c) row[c] = (rok[ky] && cok[c]) ? row[c] : 0.f;
 #pragma unroll
-                    for (int ci = 0; ci < CI_T; ++ci) acc[ci] = fmaf(v, s_w[co][ky * K + kx][ci], acc[ci]);
-                }
+                for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                    for (int ci = 0; ci < CI_T; ++ci) {
+                        const float wv = s_w[co][ky * K + kx][ci];
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) acc[j][ci] = fmaf(row[K - 1 - kx + j], wv, acc[j][ci]);
+                    }
             }
         }
         __syncthreads();
@@ -240,11 +291,13 @@ convx_dgrad_kernel(const float* __restrict__ dy, int N, int Cout, int Ho, int Wo
     if (!active) return;
     float* o = dXq + (splitK > 1 ? (size_t)blockIdx.z * ((size_t)N * Cin * Hq * Wq) : 0);   // split: partials for sum_partials_kernel
 #pragma unroll
-    for (int ci = 0; ci < CI_T; ++ci)
-        if (ci0 + ci < Cin) {
-            float* q = o + ((size_t)(n * Cin + ci0 + ci) * Hq + qy) * Wq + qx;
-            *q = (accumulate && splitK == 1) ? *q + acc[ci] : acc[ci];
-        }
+    for (int j = 0; j < PX; ++j)
+#pragma unroll
+        for (int ci = 0; ci < CI_T; ++ci)
+            if (ci0 + ci < Cin && qx0 + j < Wq) {
+                float* q = o + ((size_t)(n * Cin + ci0 + ci) * Hq + qy) * Wq + qx0 + j;
+                *q = (accumulate && splitK == 1) ? *q + acc[j][ci] : acc[j][ci];
+            }
 }
 
 // adjoint of nn.ReflectionPad2d(p): dX[y, x] (=|+=) sum of dXq over (y, x) and its mirror images in the border of width p
@@ -401,6 +454,7 @@ static __global__ void __launch_bounds__(GENX_MAX_CH) update_running_x_kernel(Ru
 // host: launch helpers
 // -------------------------------------------------------------------------------------------------
 static inline int chan_tile(int c) { return c <= 4 ? 4 : (c <= 8 ? 8 : 16); }
+static inline int px_per_thread(int K, int S) { return (S == 1 && K >= 5) ? 2 : 1; }   // == XPx<K, S>::value
 static inline int elementwise_blocks(size_t total, int per_sm) {
     const size_t b = (total + 255) / 256, cap = (size_t)148 * per_sm;
     return (int)(b < cap ? (b ? b : 1) : cap);
@@ -439,8 +493,9 @@ static int launch_convx_fwd(int K, int S, const float* x, int N, int Cin, int Hi
                             size_t split_cap, cudaStream_t st) {
     const int ct = chan_tile(Cout);
     const size_t out_elems = (size_t)N * Cout * Ho * Wo;
-    const int sk = (fin.konst && split) ? pick_split(N * Ho * Wo, Cout, ct, Cin, out_elems, split_cap) : 1;
-    dim3 grid(ceil_div(N * Ho * Wo, XCONV_THREADS), ceil_div(Cout, ct), sk);
+    const int P = N * Ho * ceil_div(Wo, px_per_thread(K, S));          // threads: one per pixel group (XPx)
+    const int sk = (fin.konst && split) ? pick_split(P, Cout, ct, Cin, out_elems, split_cap) : 1;
+    dim3 grid(ceil_div(P, XCONV_THREADS), ceil_div(Cout, ct), sk);
     float* dst = sk > 1 ? split : y;
     float* stats = sk > 1 ? nullptr : stats_part;
     BnFin fin_conv = fin;
@@ -468,8 +523,9 @@ static int launch_convx_dgrad(int K, int S, const float* dy, int N, int Cout, in
     const int acc_k = ext ? 0 : accumulate;
     const int ct = chan_tile(Cin);
     const size_t total_q = (size_t)N * Cin * Hq * Wq;
-    const int sk = pick_split(N * Hq * Wq, Cin, ct, Cout, total_q, split_cap);
-    dim3 grid(ceil_div(N * Hq * Wq, XCONV_THREADS), ceil_div(Cin, ct), sk);
+    const int P = N * Hq * ceil_div(Wq, px_per_thread(K, S));          // threads: one per pixel group (XPx)
+    const int sk = pick_split(P, Cin, ct, Cout, total_q, split_cap);
+    dim3 grid(ceil_div(P, XCONV_THREADS), ceil_div(Cin, ct), sk);
     float* kdst = sk > 1 ? split : dst;
 #define XD(KK, SS, CT) SPLICE_CHECK_CUDA(launch_pdl(convx_dgrad_kernel<KK, SS, CT>, grid, dim3(XCONV_THREADS), 0, st, dy, N, Cout, Ho, Wo, Wt, Cin, kdst, Hq, Wq, ext, acc_k, sk))
 #define XD3(KK, SS) do { if (ct == 4) XD(KK, SS, 4); else if (ct == 8) XD(KK, SS, 8); else XD(KK, SS, 16); } while (0)
