@@ -328,7 +328,8 @@ static __global__ void __launch_bounds__(256) reflect_fold_kernel(const float* _
 //   A CTA owns 16 output channels x 8 input channels x K taps of row ky and walks 8 x 32 pixel tiles: the input rows the
 //   tile's output rows meet through filter row ky (producer BatchNorm + LeakyReLU and the padding applied while staging) and
 //   the dy tile (pixel-major) in shared memory. A warp visits every 8th pixel; its 32 threads are 4 output-channel quads x
-//   8 input channels, each with 4 x K accumulators: one 128-bit load of dy + K loads of x for 4*K FMAs.
+//   8 input channels, each with 4 x K accumulators: one 128-bit load of dy + K loads of x for 4*K FMAs (stride 1: two adjacent
+//   pixels per visit, two loads of dy + K + 1 loads of x for 8*K FMAs).
 // -------------------------------------------------------------------------------------------------
 template <int K, int S>
 static __global__ void __launch_bounds__(256)
@@ -339,6 +340,7 @@ convx_wgrad_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf 
     constexpr int IW = (TW - 1) * S + K, IWP = IW + 1;
     constexpr int SXA = (CI_T * TH * IWP + 3) & ~3;
     constexpr int RS = 4 * K + 4;
+    constexpr int PXW = (S == 1 && K >= 3) ? 2 : 1;          // pixels per visit of the accumulation loop
     constexpr int SM_A = SXA + TH * TW * XDYP, SM_B = 8 * 32 * RS;
     __shared__ __align__(16) float smem[SM_A > SM_B ? SM_A : SM_B];
     float (*s_x)[TH][IWP] = reinterpret_cast<float (*)[TH][IWP]>(smem);
@@ -388,17 +390,36 @@ convx_wgrad_kernel(const float* __restrict__ x, int Cin, int Hin, int Win, InTf 
             *reinterpret_cast<float4*>(s_dy + pix * XDYP + c4) = v;
         }
         __syncthreads();
-        for (int p = g; p < TH * TW; p += 8) {
-            const int py = p / TW, px = p % TW;
-            const float4 d4 = *reinterpret_cast<const float4*>(s_dy + p * XDYP + cos);
-            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        if (PXW == 2) {
+            // stride 1: two horizontally adjacent pixels per visit share K - 1 of their K input columns
+            for (int p2 = g; p2 < TH * TW / 2; p2 += 8) {
+                const int py = p2 / (TW / 2), px = (p2 % (TW / 2)) * 2;
+                const float4 da = *reinterpret_cast<const float4*>(s_dy + (py * TW + px) * XDYP + cos);
+                const float4 db = *reinterpret_cast<const float4*>(s_dy + (py * TW + px + 1) * XDYP + cos);
+                const float d0[4] = {da.x, da.y, da.z, da.w}, d1[4] = {db.x, db.y, db.z, db.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bacc[j] += d[j];
+                for (int j = 0; j < 4; ++j) bacc[j] += d0[j] + d1[j];
+                float xr[K + 1];
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const float xv = s_x[ci][py][px * S + kx];
+                for (int c = 0; c < K + 1; ++c) xr[c] = s_x[ci][py][px + c];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j][kx] = fmaf(d[j], xv, acc[j][kx]);
+                for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][kx] = fmaf(d1[j], xr[kx + 1], fmaf(d0[j], xr[kx], acc[j][kx]));
+            }
+        } else {
+            for (int p = g; p < TH * TW; p += 8) {
+                const int py = p / TW, px = p % TW;
+                const float4 d4 = *reinterpret_cast<const float4*>(s_dy + p * XDYP + cos);
+                const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bacc[j] += d[j];
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float xv = s_x[ci][py][px * S + kx];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][kx] = fmaf(d[j], xv, acc[j][kx]);
+                }
             }
         }
         __syncthreads();
