@@ -172,21 +172,29 @@ def _loop(args, net, net_input_saved, extract_feature, ref_feature, optimizer, c
     return net, torch.stack(losses).cpu() if losses else torch.empty(0)
 
 
+# the reference script's command line (inversion.py:77-92): flag, type, default, meaning
+_CLI = (
+    ("feature", str, None, "which DINO-ViT feature of the image to invert: 'cls' ([CLS] token) or 'keys'"),
+    ("layer", int, 11, "transformer block the feature is taken from (0-11)"),
+    ("dino_model_name", str, "dino_vitb8", "dino_vits16 | dino_vits8 | dino_vitb16 | dino_vitb8"),
+    ("image_path", str, "datasets/feature_visualization/limes.jpeg", "image whose feature is inverted"),
+    ("save_path", str, None, "where the current result image is written every --log_freq iterations (required)"),
+    ("log_freq", int, 100, "iterations between two result images"),
+    ("input_depth", int, 32, "channels of the fixed noise tensor the generator maps to an image"),
+    ("LR", float, 0.01, "Adam learning rate"),
+    ("n_iter", int, 20000, "optimisation iterations"),
+    ("reduce_noise_stage_1_iter", int, 10000, "'cls' mode: input noise of scale 10 before this iteration ..."),
+    ("reduce_noise_stage_2_iter", int, 15000, "... of scale 2 before this one, 0.5 afterwards"),
+)
+
+
 def build_parser() -> ArgumentParser:
-    parser = ArgumentParser()
-    parser.add_argument("--feature", type=str, help='DINO-ViT feature to invert. options: cls | keys')
-    parser.add_argument("--layer", type=int, default=11,
-                        help='Transformer layer from which to extract the feature, between 0-11')
-    parser.add_argument("--dino_model_name", type=str, default='dino_vitb8')
-    parser.add_argument("--image_path", type=str, default='datasets/feature_visualization/limes.jpeg',
-                        help='path to the image to be used for the inversion.')
-    parser.add_argument("--save_path", type=str, required=True, help='path to save the result.')
-    parser.add_argument("--log_freq", type=int, default=100)
-    parser.add_argument("--input_depth", type=int, default=32)
-    parser.add_argument("--LR", type=float, default=0.01)
-    parser.add_argument("--n_iter", type=int, default=20000)
-    parser.add_argument("--reduce_noise_stage_1_iter", type=int, default=10000)
-    parser.add_argument("--reduce_noise_stage_2_iter", type=int, default=15000)
+    parser = ArgumentParser(description="DINO-ViT feature inversion on the splice_b200 engines (same options as the reference script)")
+    for flag, kind, default, text in _CLI:
+        if flag == "save_path":
+            parser.add_argument("--" + flag, type=kind, required=True, help=text)
+        else:
+            parser.add_argument("--" + flag, type=kind, default=default, help=text)
     return parser
 
 

@@ -285,3 +285,18 @@ def test_inversion_noise_feed_keeps_the_reference_stream():
     got = [feed.next() for _ in range(6)]
     feed.close()
     assert all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+def test_inversion_cli_matches_the_reference_script():
+    """Same options, types and defaults as the reference's inversion.py:77-92 (checked against its parser in the build
+    container; the expected values are spelled out here because /root/reference does not travel)."""
+    from splice_b200.inversion import NET_ARGS, build_parser
+
+    got = vars(build_parser().parse_args(["--save_path", "o.png", "--feature", "keys"]))
+    assert got == {"feature": "keys", "layer": 11, "dino_model_name": "dino_vitb8",
+                   "image_path": "datasets/feature_visualization/limes.jpeg", "save_path": "o.png", "log_freq": 100,
+                   "input_depth": 32, "LR": 0.01, "n_iter": 20000, "reduce_noise_stage_1_iter": 10000,
+                   "reduce_noise_stage_2_iter": 15000}
+    with pytest.raises(SystemExit):
+        build_parser().parse_args(["--feature", "cls"])          # --save_path is required
+    assert NET_ARGS["filter_size_down"] == [7, 7, 5, 5, 3, 3] and NET_ARGS["pad"] == "reflection"   # inversion.py:21-25
