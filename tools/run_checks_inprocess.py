@@ -1,5 +1,7 @@
-"""One-process GPU run used at the end of round 2 (GPU budget nearly spent): the new generator_inversion_variant check, then the
-default generator's checks and one full-step check (their kernels moved to gen_kernels.cuh: SASS unchanged, confirmed here), smoke."""
+"""Runs the named checks of tools/gpu_checks.py in ONE process (tools/gpu_checks.py itself isolates every check in a subprocess,
+which costs a torch import each - too slow for a short gpurun call), then __graft_entry__.smoke(). Default selection: the generator
+checks and one full-step check. Writes gpurun_out/checks_inprocess.json.
+    python tools/run_checks_inprocess.py [check names ...]"""
 import json
 import sys
 import time
@@ -26,7 +28,7 @@ for n in names:
     rec["secs"] = time.time() - t0
     report.append(rec)
     print(("PASS " if rec["ok"] else "FAIL ") + n, f"{rec['secs']:.1f}s", flush=True)
-    (OUT / "checks_r2final.json").write_text(json.dumps(report, indent=1, default=str))
+    (OUT / "checks_inprocess.json").write_text(json.dumps(report, indent=1, default=str))
 try:
     import __graft_entry__
 
