@@ -1,9 +1,14 @@
 """Host-side logic that needs no GPU: resize-size rule, weight packing, generator tree / init parity with the
 reference (golden), schedulers, loud failure without CUDA."""
 import ctypes as C
+import subprocess
+import sys
+from pathlib import Path
 
 import pytest
 import torch
+
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_resized_hw_matches_oracle_rule():
@@ -300,3 +305,21 @@ def test_inversion_cli_matches_the_reference_script():
     with pytest.raises(SystemExit):
         build_parser().parse_args(["--feature", "cls"])          # --save_path is required
     assert NET_ARGS["filter_size_down"] == [7, 7, 5, 5, 3, 3] and NET_ARGS["pad"] == "reflection"   # inversion.py:21-25
+
+
+@pytest.mark.skipif(not Path("/root/reference").exists(), reason="needs the reference checkout (build container only)")
+def test_reference_scripts_import_over_the_module_swap():
+    """with install_as_reference_modules() the reference's OWN train.py and inversion.py import and bind the
+    splice_b200 classes (every name they import exists in the mirrors). Running them needs a GPU; importing does not."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(1, '/root/reference')\n"
+        "import splice_b200; splice_b200.install_as_reference_modules()\n"
+        "import train, inversion\n"
+        "import splice_b200.models.model as M, splice_b200.util.losses as L, splice_b200.models.extractor as E\n"
+        "import splice_b200.models.unet.skip as S, splice_b200.data.Dataset as D\n"
+        "assert train.Model is M.Model and train.LossG is L.LossG and train.SingleImageDataset is D.SingleImageDataset\n"
+        "assert inversion.VitExtractor is E.VitExtractor and inversion.skip is S.skip\n"
+        "assert train.__file__.startswith('/root/reference') and inversion.__file__.startswith('/root/reference')\n"
+        "print('ok')\n" % str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-1500:]
