@@ -13,14 +13,17 @@ import torch  # noqa: E402
 from splice_b200.inversion import NET_ARGS as INVERSION_ARGS  # noqa: E402
 from splice_b200.models.unet.skip import skip  # noqa: E402
 
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"      # racecheck is slow: the inversion network only, one pass
 torch.manual_seed(0)
 for net, shape in ((skip(32, 3, **INVERSION_ARGS), (1, 32, 67, 90)),
                    (skip(5, 2, num_channels_down=[8, 12], num_channels_up=[8, 12], num_channels_skip=[3, 5], filter_size_down=[5, 3],
                          filter_size_up=[3, 7], filter_skip_size=3, need_sigmoid=False, pad="zero"), (2, 5, 45, 62))):
     net = net.cuda()
     x = torch.randn(*shape, device="cuda")
-    for _ in range(2):
+    for _ in range(1 if quick else 2):
         y = net(x)
         y.square().mean().backward()
     torch.cuda.synchronize()
     print("ok", shape, float(y.mean()), flush=True)
+    if quick:
+        break
