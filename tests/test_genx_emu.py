@@ -195,3 +195,57 @@ def test_inversion_engine_matches_reference_golden(emu_backend):
     assert not bad, bad
     bad = [k for k, v in net.state_dict().items() if k in gold["buffers"] and not _close(gold["buffers"][k], v.float(), 1e-3)]
     assert not bad, bad
+
+
+def test_glue_lifecycle(emu_backend):
+    """NativeSkipX's host glue on the emulated engine: deepcopy gives an independent module with its own engine, load_state_dict /
+    in-place parameter updates are seen by the next pass, a foreign .grad tensor is adopted (and accumulated into), a pass replaced
+    by a later forward refuses its backward, no_grad forwards keep nothing."""
+    from splice_b200.models.unet.skip import skip
+    from tools.genx_compare import randomise
+
+    torch.manual_seed(30)
+    net = skip(4, 3, num_channels_down=[8, 8], num_channels_up=[8, 8], num_channels_skip=[2, 2], filter_size_down=[3, 5],
+               filter_size_up=[5, 3], pad="reflection")
+    randomise(net, 31)
+    x = torch.randn(1, 4, 19, 26, generator=torch.Generator().manual_seed(32))
+    ref = lambda m: nn.Sequential.forward(copy.deepcopy(m), x).detach()      # noqa: E731  (torch modules on a copy)
+
+    y0 = net(x)
+    assert (y0 - ref(net)).abs().max().item() < 1e-5
+    twin = copy.deepcopy(net)                         # after the engine exists: the copy must not share it
+    assert twin._eng is None and twin._flat_grad is None
+    with torch.no_grad():
+        for p in twin.parameters():
+            p.mul_(1.1)
+    assert (twin(x) - ref(twin)).abs().max().item() < 1e-5
+    assert (net(x) - y0).abs().max().item() < 1e-6    # the original is unaffected by its twin's engine
+
+    sd = {k: v.clone() for k, v in twin.state_dict().items()}
+    net.load_state_dict(sd)                           # in-place copy into the bound tensors
+    assert (net(x) - ref(twin)).abs().max().item() < 1e-5
+
+    # a gradient tensor assigned from outside is adopted into the flat buffer and accumulated into
+    for p in net.parameters():
+        p.grad = None
+    first = next(net.parameters())
+    first.grad = torch.full_like(first, 0.25)
+    y = net(x)
+    y.sum().backward()
+    want = copy.deepcopy(net)
+    for p in want.parameters():
+        p.grad = None
+    nn.Sequential.forward(want, x).sum().backward()
+    g_want = next(want.parameters()).grad
+    assert torch.allclose(first.grad, g_want + 0.25, atol=1e-4 * max(1.0, g_want.abs().max().item()))
+    assert first.grad.data_ptr() == net._grad_views[0].data_ptr()
+
+    # a later forward replaces the kept pass: the older output's backward must say so instead of using the wrong activations
+    ya = net(x)
+    yb = net(x)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        ya.sum().backward()
+    yb.sum().backward()
+    with torch.no_grad():
+        yc = net(x)
+    assert not yc.requires_grad and net._kept_token is None
